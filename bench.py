@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native large-steps hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload plane1000|...]
+
+metric   : from_differential solves/sec @ 1M verts  (BASELINE.json)
+step     : one from_differential solve of a (V,3) right-hand side (forward solve of the optimisation step)
+workload : BASELINE config 3 -- plane 1000x1000 (V = 1,000,000, nnz(M) = 6,992,002), uniform Laplacian, alpha = 0.95,
+           3-RHS Jacobi-PCG to rtol 1e-7 from a cold start -- one mesh per GPU (seed = rank) at every N: weak scaling,
+           no collective on the solve path; NCCL only gathers a checksum at the end.
+value    : whole-job solves/s with the right-hand sides already in HBM (CUDA events, max over ranks)
+e2e      : same through the public API with HOST (pinned) buffers: H2D of u and D2H of v inside the timed region
+roofline : the in-solver SpMM+dot kernel timed alone with CUDA events, rotating over 4 copies of the matrix and
+           vectors (336 MB > 126 MB L2) so every launch streams from HBM; algorithmic bytes 8 nnz + 4 (V+1) + 8 k V
+cpu_baseline / --impl reference : the oracle's direct solve (SuperLU fp32, symmetric mode -- the stand-in for the
+           reference's cholespy/CHOLMOD CholeskySolver, which is not installable offline), factorisation untimed.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "large-steps-pytorch_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "from_differential solves/sec @1M verts"
+WORKLOADS = {
+    "plane1000": dict(kind="plane", n=1000, alpha=0.95, desc="plane 1000x1000, V=1000000, nnz=6992002, uniform L, alpha=0.95 (BASELINE config 3)"),
+    "plane500": dict(kind="plane", n=500, alpha=0.95, desc="plane 500x500, V=250000, nnz=1746002, uniform L, alpha=0.95 (BASELINE config 4, one per GPU)"),
+    "plane2000": dict(kind="plane", n=2000, alpha=0.95, desc="plane 2000x2000, V=4000000, uniform L, alpha=0.95 (working set >> L2)"),
+    "icosphere": dict(kind="ico", level=4, lam=10.0, desc="icosphere level 4, V=2562, uniform L, lambda=10 (BASELINE config 1)"),
+    "bunny": dict(kind="bunny", lam=19.0, desc="bunny.obj subdivided x2, V=52786, cot L, lambda=19 (BASELINE config 2)"),
+}
+RTOL = 1e-7
+
+
+def build_mesh(wl, seed):
+    from largesteps_b200 import workloads as W
+    if wl["kind"] == "plane":
+        v, f = W.plane(wl["n"], seed=seed)
+        return v, f, dict(lambda_=1.0, alpha=wl["alpha"])
+    if wl["kind"] == "ico":
+        v, f = W.icosphere(wl["level"])
+        return v, f, dict(lambda_=wl["lam"])
+    d = np.load(os.path.join(ROOT, "tests", "golden", "bunny_mesh.npz"))
+    v, f = W.subdivide(*W.subdivide(d["verts"], d["faces"].astype(np.int64)))
+    return v.astype(np.float32), f, dict(lambda_=wl["lam"], cotan=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed regions (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.path = f"/tmp/ls_clocks_{os.getpid()}.csv"
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()           # exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, pw = [], [], []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        seen = set()
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    seen.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(seen),
+                   "samples": len(sm), "power_w_max": max(pw)}
+        return out
+
+
+def cpu_direct_baseline(v, f, kw, b_list, solves):
+    """Oracle leg: SuperLU fp32 direct solve on this box's host cores (factorisation untimed)."""
+    import oracle
+    t0 = time.perf_counter()
+    r, c, val, V = oracle.compute_matrix(v, f, **kw)
+    t_asm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ds = oracle.DirectSolver(r, c, val, V, dtype=np.float32)
+    t_fac = time.perf_counter() - t0
+    ts, x = [], None
+    for i in range(solves):
+        b = b_list[i % len(b_list)]
+        t0 = time.perf_counter()
+        x = ds.solve(b)
+        ts.append(time.perf_counter() - t0)
+    return dict(t_assembly_s=t_asm, t_factor_s=t_fac, t_solve_s=ts, factor_nnz=ds.factor_nnz, x_last=x, solver=ds)
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args, wl, wl_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    v, f, kw = build_mesh(wl, seed=0)
+    import oracle
+    r, c, val, V = oracle.compute_matrix(v, f, **kw)
+    A = oracle.coo_to_scipy(r, c, val, V, dtype=np.float32)
+    rng = np.random.default_rng(100)
+    bs = [(A @ (v + rng.normal(0, 0.01, v.shape).astype(np.float32))).astype(np.float32) for _ in range(2)]
+    t0 = time.perf_counter()
+    ds = oracle.DirectSolver(r, c, val, V, dtype=np.float32)
+    t_fac = time.perf_counter() - t0
+    for i in range(args.warmup):
+        ds.solve(bs[i % 2])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ds.solve(bs[i % 2])
+    dt = time.perf_counter() - t0
+    val_sps = args.steps / dt
+    sample = (f"{args.steps} direct solves of a (V,3) fp32 RHS at V={V} after an untimed {t_fac:.1f} s factorisation "
+              f"(scipy SuperLU, symmetric mode, MMD(A^T+A); stand-in for cholespy/CHOLMOD which is not installable offline)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val_sps, "unit": "solves/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl_name, "desc": wl["desc"], "rhs_columns": 3, "solver": "CPU direct solve (oracle port of the reference Cholesky path)"},
+        "cpu_baseline": {"value": val_sps, "unit": "solves/s", "cores": 1, "kind": "port", "sample": sample,
+                         "cpu": cpu_model(), "host_cores": os.cpu_count(), "factor_s": t_fac},
+        "e2e": {"value": val_sps, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(args, wl, wl_name):
+    import torch
+    import torch.distributed as dist
+    from largesteps_b200 import _native as N, distributed as D
+    from largesteps_b200.geometry import compute_matrix
+    from largesteps_b200.parameterize import to_differential, from_differential, _cache
+    from largesteps_b200.solvers import PCGSolver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a GPU (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N.lib()
+
+    # ---- setup (untimed): one mesh per rank -----------------------------------------------------------
+    v, f, kw = build_mesh(wl, seed=rank)
+    V = v.shape[0]
+    tv = torch.from_numpy(v).to(dev)
+    tf = torch.from_numpy(f).to(dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    M = compute_matrix(tv, tf, **kw)
+    torch.cuda.synchronize()
+    t_assemble = time.perf_counter() - t0
+    nnz = M._nnz()
+    R = 4
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    us = []
+    for i in range(R):
+        vv = tv + 0.01 * torch.randn(V, 3, device=dev, generator=gen)
+        us.append((to_differential(M, vv) + 0.01 * torch.randn(V, 3, device=dev, generator=gen)).contiguous())
+    t0 = time.perf_counter()
+    x = from_differential(M, us[0], "Cholesky")          # builds + caches the solver handle
+    torch.cuda.synchronize()
+    t_first = time.perf_counter() - t0
+    solver = _cache[(id(M), "Cholesky")][0]
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        D.barrier()
+        n0 = N.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        D.barrier()
+        ms = e0.elapsed_time(e1)
+        return D.max_over_ranks(ms, device=dev), N.launch_count() - n0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- value: device-resident right-hand sides ---------------------------------------------------------
+    iters = []
+
+    def step_dev(i):
+        with torch.no_grad():
+            from_differential(M, us[i % R], "Cholesky")
+        iters.append(solver.iterations)
+
+    ms_total, launches = timed(step_dev, args.steps, args.warmup)
+    it_mean = float(np.mean(iters[-args.steps:]))
+    value = world * args.steps / (ms_total * 1e-3)
+
+    # ---- fwd+bwd pairs (what one optimiser step does: scripts/main.py:173,206) ---------------------------
+    gsmall = [(1e-4 * torch.randn(V, 3, device=dev, generator=gen)) for _ in range(2)]
+
+    def step_pair(i):
+        u = us[i % R].detach().requires_grad_(True)
+        xx = from_differential(M, u, "Cholesky")
+        xx.backward(gsmall[i % 2])
+
+    pair_steps = max(3, args.steps // 4)
+    ms_pair, _ = timed(step_pair, pair_steps, min(args.warmup, 3))
+    pairs_per_s = world * pair_steps / (ms_pair * 1e-3)
+
+    # ---- e2e: host buffers through the public API ----------------------------------------------------------
+    h_in = [u.cpu().pin_memory() for u in us]
+    h_out = torch.empty(V, 3, dtype=torch.float32).pin_memory()
+    d_u = torch.empty(V, 3, dtype=torch.float32, device=dev)
+
+    def step_e2e(i):
+        with torch.no_grad():
+            d_u.copy_(h_in[i % R], non_blocking=True)
+            xx = from_differential(M, d_u, "Cholesky")
+            h_out.copy_(xx, non_blocking=True)
+
+    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+    bytes_io = V * 3 * 4
+
+    # ---- roofline: the dominant kernel (in-solver SpMM + p.Ap) alone, HBM-cold by rotation ----------------
+    roof = None
+    if rank == 0:
+        extra = [PCGSolver(M) for _ in range(3)]
+        handles = [solver] + extra
+        L = 400
+        for h in handles:
+            h.bench_spmm(3, 2)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(L):
+            handles[i % 4].bench_spmm(3, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        us_per = 1e3 * e0.elapsed_time(e1) / L
+        # same kernel with everything L2-resident (one handle), for contrast
+        e0.record()
+        solver.bench_spmm(3, L)
+        e1.record()
+        torch.cuda.synchronize()
+        us_hot = 1e3 * e0.elapsed_time(e1) / L
+        bytes_alg = solver.spmm_bytes(3)
+        peak, peak_src = measured_peak()
+        ach = bytes_alg / (us_per * 1e-6) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+        if os.path.exists(tp) and wl_name == "plane1000":
+            try:
+                traffic = json.load(open(tp))["dram_bytes_per_launch"]
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "kernel": "lsk::spmm_tma_kernel<3,SOA,DOT>", "us_per_launch": us_per, "algorithmic_bytes": bytes_alg,
+                "peak_source": peak_src, "l2_resident_us_per_launch": us_hot,
+                "l2_resident_GBs": bytes_alg / (us_hot * 1e-6) / 1e9,
+                "how": "CUDA events over 400 back-to-back launches rotating over 4 matrix+vector copies (336 MB > L2)"}
+        del extra, handles
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- trivial gather (the only collective): checksum of every rank's last solution ---------------------
+    with torch.no_grad():
+        xs = from_differential(M, us[0], "Cholesky")
+    chk = D.gather_solutions(xs.double().sum(dim=0, keepdim=True).float())
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        b_host = [us[0].cpu().numpy(), us[1].cpu().numpy()]
+        nsolve = 3 if V >= 500000 else 10
+        cb = cpu_direct_baseline(v, f, kw, b_host, nsolve)
+        best = min(cb["t_solve_s"])
+        parity = float(np.linalg.norm(xs.cpu().numpy().astype(np.float64) - cb["solver"].solve(b_host[0]).astype(np.float64))
+                       / np.linalg.norm(cb["x_last"].astype(np.float64)))
+        cpu = {"value": 1.0 / best, "unit": "solves/s", "cores": 1, "kind": "port",
+               "sample": (f"{nsolve} direct solves (best of) of a (V,3) fp32 RHS at V={V} after an untimed "
+                          f"{cb['t_factor_s']:.1f} s factorisation; scipy SuperLU symmetric mode = stand-in for the "
+                          f"reference's cholespy/CHOLMOD CholeskySolver"),
+               "cpu": cpu_model(), "host_cores": os.cpu_count(), "factor_s": cb["t_factor_s"],
+               "assembly_s": cb["t_assembly_s"], "factor_nnz": cb["factor_nnz"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "desc": wl["desc"], "V": V, "nnz": nnz, "rhs_columns": 3,
+                       "solver": "Jacobi-PCG, cold start", "rtol": RTOL, "cg_iterations_mean": it_mean,
+                       "parallelism": f"{world} independent mesh(es), one per GPU, no collective on the solve path",
+                       "l2": "per-iteration working set ~200 MB > 126 MB L2 and 4 rotating right-hand sides; no explicit flush"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "extra": {"fwd_bwd_pairs_per_s": pairs_per_s, "us_per_cg_iteration": 1e3 * (ms_total / args.steps) / max(it_mean, 1),
+                      "assembly_ms": 1e3 * t_assemble, "first_solve_incl_solver_build_ms": 1e3 * t_first,
+                      "parity_rel_l2_vs_cpu_direct": parity, "checksums": chk.flatten().tolist()[:6]},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("LS_BENCH_WORKLOAD", "plane1000"), choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl, args.workload)
+    return run_b200(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

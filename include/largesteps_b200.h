@@ -1,0 +1,119 @@
+/*
+ * largesteps_b200.h -- C ABI of the B200-native large-steps hot path (libls_b200.so).
+ *
+ * Every entry point replaces a piece of the reference's Python hot path; the reference interface each one
+ * stands in for is cited as (file:line) relative to rgl-epfl/large-steps-pytorch.  The reference has no FFI
+ * of its own for this path (its device arithmetic lives in torch sparse ops and in the third-party wheel
+ * `cholespy`), so this header is the boundary a maintainer would bind with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; device pointers are raw `void*`/typed pointers into CUDA global memory of the
+ *     CURRENT device; `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *   - every function returns an `ls_status` (0 = LS_OK).  `ls_last_error()` gives a thread-local message.
+ *   - all work is stream-ordered and asynchronous unless a HOST out-pointer is documented as synchronising.
+ *   - arrays named rowptr/col/val must be 16-byte aligned and readable up to the next 16-byte boundary
+ *     past their last element (true for any cudaMalloc / torch allocation): the SpMM streams them with
+ *     1-D TMA bulk copies (cp.async.bulk), which move whole 16-byte granules.
+ *   - a handle is not thread-safe; distinct handles are independent.
+ */
+#ifndef LARGESTEPS_B200_H
+#define LARGESTEPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    LS_OK = 0,
+    LS_ERR_BAD_ARG = 1,        /* null pointer, bad size, misaligned array, k out of range            */
+    LS_ERR_CUDA = 2,           /* a CUDA runtime call failed (message in ls_last_error)                */
+    LS_ERR_BREAKDOWN = 3,      /* CG breakdown: p.Ap <= 0 or NaN (matrix not SPD / NaN input)          */
+    LS_ERR_NOT_CONVERGED = 4,  /* maxit reached before the relative residual target                    */
+    LS_ERR_UNSUPPORTED = 5,    /* configuration not supported by this build                            */
+    LS_ERR_INDEX_RANGE = 6,    /* face / COO index outside [0, V)                                      */
+    LS_ERR_WORKSPACE = 7       /* workspace too small                                                  */
+} ls_status;
+
+/* ---- library ------------------------------------------------------------------------------------- */
+int         ls_version(void);                 /* 10000*major + 100*minor + patch                        */
+const char *ls_last_error(void);              /* thread-local, never NULL                               */
+const char *ls_status_string(int status);
+/* number of kernels this library has launched since load (bench.py's `gpu_launches` evidence)          */
+uint64_t    ls_launch_count(void);
+/* persisting kernels in a graph count once per graph launch * nodes; see DESIGN.md                      */
+
+/* ---- system-matrix assembly  (replaces largesteps/geometry.py:3-133: laplacian_cot, laplacian_uniform,
+ *      compute_matrix -- torch.unique / coalesce / sparse add on the device) ------------------------------
+ * Two-phase because nnz(M) = V + 2E is only known after the directed edges have been de-duplicated.
+ *   faces      (F,3) int32 (idx_bytes=4) or int64 (idx_bytes=8), row-major, device
+ *   workspace  ls_assemble_workspace_bytes(F, V) bytes, device, 16-byte aligned; must be kept untouched
+ *              between _count and _fill
+ *   nnz_out    HOST pointer; _count synchronises the stream to write it                               */
+int ls_assemble_workspace_bytes(int64_t F, int64_t V, size_t *bytes_out);
+int ls_assemble_count(const void *faces, int idx_bytes, int64_t F, int64_t V,
+                      void *workspace, size_t workspace_bytes, int64_t *nnz_out, void *stream);
+/*   verts      (V,3) float32 device (only read when cotan != 0; geometry.py:20-41)
+ *   diag_shift 1.0f for M = I + lambda L, float(1-alpha) for M = (1-alpha) I + alpha L  (geometry.py:127-132)
+ *   scale      lambda or alpha
+ *   outputs (any group may be NULL):
+ *     coo_row, coo_col (nnz) int64 + coo_val (nnz) float32 : the coalesced, row-major sorted COO triplets
+ *                         torch.sparse_coo_tensor(...).coalesce() would hold (geometry.py:133)
+ *     csr_rowptr (V+1) int32, csr_col (nnz) int32, csr_val (nnz) float32 : the CSR the solver streams    */
+int ls_assemble_fill(const void *faces, int idx_bytes, const float *verts, int64_t F, int64_t V,
+                     int cotan, float diag_shift, float scale,
+                     void *workspace, size_t workspace_bytes, int64_t nnz,
+                     int64_t *coo_row, int64_t *coo_col, float *coo_val,
+                     int32_t *csr_rowptr, int32_t *csr_col, float *csr_val, void *stream);
+
+/* ---- COO -> CSR  (what CholeskySolver.__init__ hands to cholespy: solvers.py:33-34, M.indices(), M.values())
+ *   coo_row/coo_col: coalesced, row-major sorted int64 (nnz).  Writes rowptr (V+1) and col (nnz) int32.
+ *   Unsorted rows or out-of-range indices -> LS_ERR_INDEX_RANGE (synchronises to report it).            */
+int ls_coo_to_csr(const int64_t *coo_row, const int64_t *coo_col, int64_t nnz, int64_t V,
+                  int32_t *csr_rowptr, int32_t *csr_col, void *stream);
+
+/* ---- y = A x  (replaces torch sparse `M @ v`: parameterize.py:30 to_differential; scripts/main.py:192-195)
+ *   CSR float32 / int32;  x, y: (V,k) float32 row-major with leading dimensions ldx, ldy (>= k), k >= 1.  */
+int ls_spmm_csr_f32(int64_t V, const int32_t *rowptr, const int32_t *col, const float *val,
+                    const float *x, int64_t ldx, float *y, int64_t ldy, int k, void *stream);
+
+/* ---- preconditioned conjugate gradients  (replaces solvers.py:26-39 CholeskySolver.solve via cholespy and
+ *      solvers.py:41-126 ConjugateGradientSolver: solve M X = B for all k columns in one pass) ------------
+ *   ls_pcg_workspace_bytes: bytes of device workspace a handle for (V, nnz, k_max) needs.
+ *   ls_pcg_create: copies the CSR into the (caller-owned, 256-byte aligned) workspace in the solver's padded
+ *       streaming layout, extracts the Jacobi diagonal, balances the row partition, builds the CUDA graph.
+ *       The caller keeps `workspace` alive until ls_pcg_destroy.  Synchronises `stream`.
+ *       precond: 0 = none, 1 = Jacobi.   k_max in [1,4].
+ *   ls_pcg_solve:  b, x: (V,k) float32 row-major contiguous (ld = k); x0 = NULL for a cold start (x0 may alias x).
+ *       rtol: stop when ||r_j||_2 <= rtol * ||b_j||_2 for every column j (columns freeze independently, which
+ *       is what the reference's per-axis solves do, solvers.py:115-118).  maxit > 0.
+ *       info_dev (optional, device, 8 floats): [iterations, status, relres_0..relres_3, 0, 0] written
+ *       stream-ordered; info_host (optional, HOST, same 8 floats): if non-NULL the call synchronises and
+ *       returns LS_ERR_NOT_CONVERGED / LS_ERR_BREAKDOWN as status; if NULL the call stays asynchronous.   */
+int ls_pcg_workspace_bytes(int64_t V, int64_t nnz, int k_max, size_t *bytes_out);
+int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz,
+                  const int32_t *rowptr, const int32_t *col, const float *val,
+                  int precond, int k_max, void *workspace, size_t workspace_bytes, void *stream);
+int ls_pcg_solve(void *handle, const float *b, float *x, const float *x0, int k,
+                 float rtol, int maxit, float *info_dev, float *info_host, void *stream);
+int ls_pcg_destroy(void *handle);
+/* in-solver SpMM of the handle's own matrix copy on SoA planes, for profiling the dominant kernel:
+ *   runs `launches` back-to-back launches of the solver's SpMM+dot kernel on its internal p/Ap planes.  */
+int ls_pcg_bench_spmm(void *handle, int k, int launches, void *stream);
+/* algorithmic bytes of one in-solver SpMM launch: 8 nnz + 4 (V+1) + 8 k V  (SURVEY.md section 8 d)      */
+int64_t ls_pcg_spmm_bytes(void *handle, int k);
+
+/* ---- fused AdamUniform step  (replaces largesteps/optimize.py:17-41) ----------------------------------
+ *   n elements float32; one_minus_beta{1,2} = 1 - beta and c1 = 1 - beta1^t, c2 = 1 - beta2^t are computed by
+ *   the caller in double (as the reference's Python does) and rounded once to float.
+ *   scratch: device, >= 16 bytes, zero-initialised by the callee.                                        */
+int ls_adam_uniform_step(float *param, const float *grad, float *g1, float *g2, int64_t n,
+                         float lr, float beta1, float beta2, float one_minus_beta1, float one_minus_beta2,
+                         float c1, float c2, void *scratch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LARGESTEPS_B200_H */

@@ -1,0 +1,680 @@
+// ls_pcg.cu -- Jacobi-preconditioned conjugate gradients for M X = B, all K columns in one pass (sm_100a).
+//
+// Replaces the reference's solve plug-ins (largesteps/solvers.py:26-39 CholeskySolver -> cholespy/CHOLMOD,
+// solvers.py:41-126 ConjugateGradientSolver -> ~12 eager torch kernels + 1 host sync per iteration per axis).
+//
+// Data layout in HBM (all inside the caller-provided workspace):
+//   CSR copy  rowptr (V+1) int32, col (nnz) int32, val (nnz) fp32, padded so 16-byte TMA granules never leave it
+//   dinv      Vp fp32                      Jacobi 1/diag (0 in the padding)
+//   x r p Ap  K planes of Vp fp32 each     SoA: plane k holds column k; Vp = V rounded up to 32 (zero padded)
+//   ctrl      PcgCtrl                      device-resident scalars: the iteration never returns to the host for them
+//
+// One iteration = three kernels, every global vector read/written once per kernel:
+//   K1  Ap = A p, pAp_k = p_k.Ap_k                     (TMA-staged SpMM + deterministic grid reduction)
+//   K2  x += a p; r -= a Ap; rz' = r.(dinv r); rr = r.r (fused update + 2K dot products; last CTA does the
+//       scalar state transition: beta, convergence per column, iteration count, done flag)
+//   K3  p = dinv r + beta p
+// Columns carry their own alpha/beta and freeze independently when ||r_k|| <= rtol ||b_k||, which is exactly the
+// reference's "one CG per axis" (solvers.py:115-118) run in lock-step.  Dot products accumulate in fp64.
+// The iteration loop is a CUDA graph of CHUNK iterations replayed until the device-side `done` flag is seen.
+#include <new>
+#include <string.h>
+#include "ls_spmm_kernel.cuh"
+
+namespace lsk {
+void spmm_config(int *stages, int *cap);
+template <int K, bool SOA, bool DOT> int spmm_prepare(int stages, int cap, int *ctas_per_sm);
+template <int K, bool SOA, bool DOT> int spmm_launch(const SpmmArgs &a, int grid, cudaStream_t stream);
+int spmm_grid_for(int64_t V, int sm_count, int occ);
+}  // namespace lsk
+
+namespace {
+
+constexpr int KMAX = 4;
+constexpr int VEC_THREADS = 256;
+constexpr int CHUNK = 8;   // CG iterations per graph launch
+
+struct PcgCtrl {
+    double rz[KMAX], rz_new[KMAX], pAp[KMAX], rr[KMAX], bb[KMAX];
+    float beta[KMAX];
+    float rtol2;
+    int maxit;
+    int it;
+    int done;        // 0 running, 1 converged, 2 maxit reached, 3 breakdown
+    int conv[KMAX];  // column frozen
+    int k;
+};
+
+struct PcgHandle {
+    int64_t V, nnz, Vp;
+    int k_max, precond;
+    int device;
+    int sm_count;
+    // workspace carve-out (device)
+    int *rowptr, *col;
+    float *val, *dinv;
+    float *x, *r, *p, *Ap;
+    int *part;
+    PcgCtrl *ctrl;
+    double *part_spmm, *part_vec;
+    unsigned int *tickets;   // [0] spmm, [1] vec
+    float *info;
+    int *flags;
+    // launch geometry
+    int spmm_stages, spmm_cap, spmm_grid;
+    int vec_grid;
+    // graphs, one per K
+    cudaGraphExec_t graph[KMAX + 1];
+    cudaStream_t cap_stream;
+    int *pinned_done;        // 2 ints, host pinned
+    cudaEvent_t ev[2];
+    size_t ws_bytes;
+};
+
+struct Carve {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        size_t o = off;
+        off = ls_align_up(off + bytes, 256);
+        return o;
+    }
+};
+
+size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max, int grid_cap) {
+    Carve c;
+    int64_t Vp = (V + 31) / 32 * 32;
+    size_t o_rp = c.take((size_t)(V + 1 + 8) * 4);
+    size_t o_col = c.take((size_t)(nnz + 8) * 4);
+    size_t o_val = c.take((size_t)(nnz + 8) * 4);
+    size_t o_dinv = c.take((size_t)Vp * 4);
+    size_t o_x = c.take((size_t)Vp * 4 * k_max);
+    size_t o_r = c.take((size_t)Vp * 4 * k_max);
+    size_t o_p = c.take((size_t)Vp * 4 * k_max);
+    size_t o_Ap = c.take((size_t)Vp * 4 * k_max);
+    size_t o_part = c.take((size_t)(grid_cap + 1) * 4);
+    size_t o_ctrl = c.take(sizeof(PcgCtrl));
+    size_t o_ps = c.take((size_t)grid_cap * KMAX * 8);
+    size_t o_pv = c.take((size_t)grid_cap * 3 * KMAX * 8);
+    size_t o_tk = c.take(64);
+    size_t o_info = c.take(64);
+    size_t o_flags = c.take(64);
+    if (h && base) {
+        h->Vp = Vp;
+        h->rowptr = (int *)(base + o_rp);
+        h->col = (int *)(base + o_col);
+        h->val = (float *)(base + o_val);
+        h->dinv = (float *)(base + o_dinv);
+        h->x = (float *)(base + o_x);
+        h->r = (float *)(base + o_r);
+        h->p = (float *)(base + o_p);
+        h->Ap = (float *)(base + o_Ap);
+        h->part = (int *)(base + o_part);
+        h->ctrl = (PcgCtrl *)(base + o_ctrl);
+        h->part_spmm = (double *)(base + o_ps);
+        h->part_vec = (double *)(base + o_pv);
+        h->tickets = (unsigned int *)(base + o_tk);
+        h->info = (float *)(base + o_info);
+        h->flags = (int *)(base + o_flags);
+    }
+    return c.off;
+}
+
+constexpr int GRID_CAP = 148 * 8 * 2;   // upper bound on any persistent grid we launch (workspace sizing)
+
+// ---- setup kernels --------------------------------------------------------------------------------
+__global__ void k_pad_tail(int *rowptr, int *col, float *val, int64_t V, int64_t nnz) {
+    int t = threadIdx.x;
+    if (t < 8) {
+        rowptr[V + 1 + t] = (int)nnz;
+        col[nnz + t] = 0;
+        val[nnz + t] = 0.f;
+    }
+}
+
+__global__ void k_dinv(int64_t V, int64_t Vp, const int *__restrict__ rowptr, const int *__restrict__ col,
+                       const float *__restrict__ val, int precond, float *__restrict__ dinv, int *__restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Vp) return;
+    if (i >= V) {
+        dinv[i] = 0.f;
+        return;
+    }
+    float d = 0.f;
+    bool found = false;
+    int s = rowptr[i], e = rowptr[i + 1];
+    if (e < s) atomicOr(flags, 4);
+    for (int j = s; j < e; ++j) {
+        int c = col[j];
+        if (c < 0 || c >= V) atomicOr(flags, 1);
+        if (c == (int)i) {
+            d += val[j];
+            found = true;
+        }
+    }
+    if (!found || !(d > 0.f)) atomicOr(flags, 2);
+    dinv[i] = precond ? (1.0f / d) : 1.0f;
+}
+
+// nnz-balanced contiguous row partition: part[c] = first row r with weight(r) >= c * total / G,
+// weight(r) = 2 * rowptr[r] + 5 * r   (~ bytes/4 streamed per non-zero and per row)
+__global__ void k_partition(int64_t V, const int *__restrict__ rowptr, int G, int *__restrict__ part) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > G) return;
+    if (c == G) {
+        part[c] = (int)V;
+        return;
+    }
+    long long total = 2LL * rowptr[V] + 5LL * V;
+    long long target = total * c / G;
+    int64_t lo = 0, hi = V;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        long long w = 2LL * rowptr[mid] + 5LL * mid;
+        if (w < target) lo = mid + 1;
+        else hi = mid;
+    }
+    part[c] = (int)lo;
+}
+
+// ---- solve kernels --------------------------------------------------------------------------------
+struct VecArgs {
+    int64_t V, Vp;
+    float *x, *r, *p, *Ap;
+    const float *dinv;
+    PcgCtrl *ctrl;
+    double *partials;
+    unsigned int *ticket;
+};
+
+// cold start: x = 0, r = b, p = z = dinv r;  warm (stage 2): r = b - Ap (Ap = A x0 from K1), p = z
+template <int K, bool WARM>
+__global__ void __launch_bounds__(VEC_THREADS) k_init(VecArgs a, const float *__restrict__ b, float rtol, int maxit) {
+    __shared__ double red[3 * K * 32 + 3 * K + 1];
+    double acc[3 * K];   // [rz | bb | rr]
+#pragma unroll
+    for (int i = 0; i < 3 * K; ++i) acc[i] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.V; i += (int64_t)gridDim.x * blockDim.x) {
+        const float di = a.dinv[i];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float bv = b[i * K + k];
+            float rv = bv;
+            if (WARM) rv = bv - a.Ap[(size_t)k * a.Vp + i];
+            else a.x[(size_t)k * a.Vp + i] = 0.f;
+            const float z = di * rv;
+            a.r[(size_t)k * a.Vp + i] = rv;
+            a.p[(size_t)k * a.Vp + i] = z;
+            acc[k] += (double)rv * (double)z;
+            acc[K + k] += (double)bv * (double)bv;
+            acc[2 * K + k] += (double)rv * (double)rv;
+        }
+    }
+    double tot[3 * K];
+    const bool last = ls_grid_reduce<3 * K>(acc, tot, a.partials, a.ticket, red, threadIdx.x, VEC_THREADS, 1,
+                                            blockIdx.x, gridDim.x);
+    if (last && threadIdx.x == 0) {
+        PcgCtrl *c = a.ctrl;
+        int all = 1;
+        const double rtol2 = (double)rtol * (double)rtol;
+        for (int k = 0; k < K; ++k) {
+            c->rz[k] = tot[k];
+            c->rz_new[k] = tot[k];
+            c->bb[k] = tot[K + k];
+            c->rr[k] = tot[2 * K + k];
+            c->pAp[k] = 1.0;
+            c->beta[k] = 0.f;
+            const int cv = tot[2 * K + k] <= rtol2 * tot[K + k];   // b_k == 0, or the warm start is already good enough
+            c->conv[k] = cv;
+            all &= cv;
+        }
+        for (int k = K; k < KMAX; ++k) {
+            c->conv[k] = 1;
+            c->rr[k] = 0.0;
+            c->bb[k] = 0.0;
+        }
+        c->rtol2 = rtol * rtol;
+        c->maxit = maxit;
+        c->it = 0;
+        c->k = K;
+        c->done = all ? 1 : 0;
+    }
+}
+
+// warm start stage 1: x = x0 (AoS -> SoA), p = x0 (SpMM input), done = 0 so that K1 runs
+template <int K>
+__global__ void __launch_bounds__(VEC_THREADS) k_warm_load(VecArgs a, const float *__restrict__ x0) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.V; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float v = x0[i * K + k];
+            a.x[(size_t)k * a.Vp + i] = v;
+            a.p[(size_t)k * a.Vp + i] = v;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ctrl->done = 0;
+}
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+// K2: x += alpha p, r -= alpha Ap, rz' = r.(dinv r), rr = r.r ; last CTA: scalar state transition
+template <int K>
+__global__ void __launch_bounds__(VEC_THREADS) k_update(VecArgs a) {
+    __shared__ double red[2 * K * 32 + 2 * K + 1];
+    PcgCtrl *c = a.ctrl;
+    if (*reinterpret_cast<volatile int *>(&c->done) != 0) return;
+    float alpha[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double pAp = c->pAp[k];
+        alpha[k] = (c->conv[k] || !(pAp > 0.0)) ? 0.f : (float)(c->rz[k] / pAp);
+    }
+    double acc[2 * K];
+#pragma unroll
+    for (int i = 0; i < 2 * K; ++i) acc[i] = 0.0;
+    const int64_t n4 = a.Vp >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 d = ld4(a.dinv + 4 * i);
+        float4 xv[K], pv[K], rv[K], qv[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const size_t o = (size_t)k * a.Vp + 4 * i;
+            xv[k] = ld4(a.x + o);
+            pv[k] = ld4(a.p + o);
+            rv[k] = ld4(a.r + o);
+            qv[k] = ld4(a.Ap + o);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const size_t o = (size_t)k * a.Vp + 4 * i;
+            const float al = alpha[k];
+            xv[k].x = fmaf(al, pv[k].x, xv[k].x);
+            xv[k].y = fmaf(al, pv[k].y, xv[k].y);
+            xv[k].z = fmaf(al, pv[k].z, xv[k].z);
+            xv[k].w = fmaf(al, pv[k].w, xv[k].w);
+            rv[k].x = fmaf(-al, qv[k].x, rv[k].x);
+            rv[k].y = fmaf(-al, qv[k].y, rv[k].y);
+            rv[k].z = fmaf(-al, qv[k].z, rv[k].z);
+            rv[k].w = fmaf(-al, qv[k].w, rv[k].w);
+            st4(a.x + o, xv[k]);
+            st4(a.r + o, rv[k]);
+            const float r2x = rv[k].x * rv[k].x, r2y = rv[k].y * rv[k].y, r2z = rv[k].z * rv[k].z, r2w = rv[k].w * rv[k].w;
+            acc[k] += (double)(d.x * r2x) + (double)(d.y * r2y) + (double)(d.z * r2z) + (double)(d.w * r2w);
+            acc[K + k] += (double)r2x + (double)r2y + (double)r2z + (double)r2w;
+        }
+    }
+    double tot[2 * K];
+    const bool last = ls_grid_reduce<2 * K>(acc, tot, a.partials, a.ticket, red, threadIdx.x, VEC_THREADS, 1,
+                                            blockIdx.x, gridDim.x);
+    if (last && threadIdx.x == 0) {
+        int all = 1, bad = 0;
+        for (int k = 0; k < K; ++k) {
+            if (c->conv[k]) continue;
+            const double pAp = c->pAp[k];
+            if (!(pAp > 0.0) || !(tot[k] == tot[k])) bad = 1;   // not SPD, or NaN crept in
+            const double rz_old = c->rz[k];
+            c->beta[k] = (rz_old > 0.0) ? (float)(tot[k] / rz_old) : 0.f;
+            c->rz[k] = tot[k];
+            c->rz_new[k] = tot[k];
+            c->rr[k] = tot[K + k];
+            const int cv = tot[K + k] <= (double)c->rtol2 * c->bb[k];
+            c->conv[k] = cv;
+            if (cv) c->beta[k] = 0.f;
+            all &= cv;
+        }
+        const int it = c->it + 1;
+        c->it = it;
+        if (bad) c->done = 3;
+        else if (all) c->done = 1;
+        else if (it >= c->maxit) c->done = 2;
+    }
+}
+
+// K3: p = dinv r + beta p
+template <int K>
+__global__ void __launch_bounds__(VEC_THREADS) k_pupdate(VecArgs a) {
+    PcgCtrl *c = a.ctrl;
+    if (*reinterpret_cast<volatile int *>(&c->done) != 0) return;
+    float beta[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) beta[k] = c->beta[k];
+    const int64_t n4 = a.Vp >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 d = ld4(a.dinv + 4 * i);
+        float4 pv[K], rv[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const size_t o = (size_t)k * a.Vp + 4 * i;
+            pv[k] = ld4(a.p + o);
+            rv[k] = ld4(a.r + o);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const size_t o = (size_t)k * a.Vp + 4 * i;
+            const float be = beta[k];
+            pv[k].x = fmaf(be, pv[k].x, d.x * rv[k].x);
+            pv[k].y = fmaf(be, pv[k].y, d.y * rv[k].y);
+            pv[k].z = fmaf(be, pv[k].z, d.z * rv[k].z);
+            pv[k].w = fmaf(be, pv[k].w, d.w * rv[k].w);
+            st4(a.p + o, pv[k]);
+        }
+    }
+}
+
+// x (SoA) -> out (AoS), info
+template <int K>
+__global__ void __launch_bounds__(VEC_THREADS) k_final(VecArgs a, float *__restrict__ out, float *__restrict__ info) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.V; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[i * K + k] = a.x[(size_t)k * a.Vp + i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const PcgCtrl *c = a.ctrl;
+        float tmp[8];
+        tmp[0] = (float)c->it;
+        tmp[1] = (float)c->done;
+        for (int k = 0; k < KMAX; ++k) tmp[2 + k] = (k < K && c->bb[k] > 0.0) ? (float)sqrt(c->rr[k] / c->bb[k]) : 0.f;
+        tmp[6] = tmp[7] = 0.f;
+        for (int j = 0; j < 8; ++j)
+            if (info) info[j] = tmp[j];
+    }
+}
+
+VecArgs vec_args(PcgHandle *h, int which_ticket) {
+    VecArgs a;
+    a.V = h->V;
+    a.Vp = h->Vp;
+    a.x = h->x;
+    a.r = h->r;
+    a.p = h->p;
+    a.Ap = h->Ap;
+    a.dinv = h->dinv;
+    a.ctrl = h->ctrl;
+    a.partials = h->part_vec;
+    a.ticket = h->tickets + which_ticket;
+    return a;
+}
+
+lsk::SpmmArgs spmm_args(PcgHandle *h, bool with_done) {
+    lsk::SpmmArgs s{};
+    s.V = (int)h->V;
+    s.stages = h->spmm_stages;
+    s.cap = h->spmm_cap;
+    s.rowptr = h->rowptr;
+    s.col = h->col;
+    s.val = h->val;
+    s.x = h->p;
+    s.y = h->Ap;
+    s.ldx = h->Vp;
+    s.ldy = h->Vp;
+    s.part = h->part;
+    s.done = with_done ? &h->ctrl->done : nullptr;
+    s.partials = h->part_spmm;
+    s.ticket = h->tickets + 0;
+    s.dot_out = h->ctrl->pAp;
+    return s;
+}
+
+template <int K>
+int launch_spmm(PcgHandle *h, bool with_done, cudaStream_t s) {
+    return lsk::spmm_launch<K, true, true>(spmm_args(h, with_done), h->spmm_grid, s);
+}
+
+template <int K>
+int launch_iteration(PcgHandle *h, cudaStream_t s) {
+    int rc = launch_spmm<K>(h, true, s);
+    if (rc) return rc;
+    k_update<K><<<h->vec_grid, VEC_THREADS, 0, s>>>(vec_args(h, 1));
+    LS_LAUNCH_CHECK();
+    k_pupdate<K><<<h->vec_grid, VEC_THREADS, 0, s>>>(vec_args(h, 1));
+    LS_LAUNCH_CHECK();
+    return LS_OK;
+}
+
+template <int K>
+int build_graph(PcgHandle *h) {
+    if (h->graph[K]) return LS_OK;
+    cudaGraph_t g = nullptr;
+    LS_CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = LS_OK;
+    for (int i = 0; i < CHUNK && rc == LS_OK; ++i) rc = launch_iteration<K>(h, h->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
+    if (rc) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+    }
+    LS_CUDA_TRY(e);
+    // launches recorded during capture were counted once; replays are counted in solve
+    e = cudaGraphInstantiate(&h->graph[K], g, 0);
+    cudaGraphDestroy(g);
+    LS_CUDA_TRY(e);
+    return LS_OK;
+}
+
+template <int K>
+int solve_k(PcgHandle *h, const float *b, float *x, const float *x0, float rtol, int maxit, float *info_dev,
+            float *info_host, cudaStream_t stream) {
+    int occ;
+    int rc = lsk::spmm_prepare<K, true, true>(h->spmm_stages, h->spmm_cap, &occ);
+    if (rc) return rc;
+    rc = build_graph<K>(h);
+    if (rc) return rc;
+    VecArgs va = vec_args(h, 1);
+    if (x0) {
+        k_warm_load<K><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, x0);
+        LS_LAUNCH_CHECK();
+        rc = launch_spmm<K>(h, false, stream);
+        if (rc) return rc;
+        k_init<K, true><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, b, rtol, maxit);
+        LS_LAUNCH_CHECK();
+    } else {
+        k_init<K, false><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, b, rtol, maxit);
+        LS_LAUNCH_CHECK();
+    }
+    // iterate: replay the CHUNK-iteration graph; the device `done` flag of chunk c-1 is checked while chunk c runs
+    // (kernels of a chunk enqueued after convergence see `done` and return immediately).
+    int launched = 0, nq = 0;
+    bool finished = false;
+    while (!finished) {
+        LS_CUDA_TRY(cudaGraphLaunch(h->graph[K], stream));
+        g_ls_launches.fetch_add(3 * CHUNK, std::memory_order_relaxed);
+        LS_CUDA_TRY(cudaMemcpyAsync(&h->pinned_done[nq & 1], &h->ctrl->done, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        LS_CUDA_TRY(cudaEventRecord(h->ev[nq & 1], stream));
+        ++nq;
+        launched += CHUNK;
+        if (nq >= 2) {
+            LS_CUDA_TRY(cudaEventSynchronize(h->ev[(nq - 2) & 1]));
+            if (h->pinned_done[(nq - 2) & 1] != 0) finished = true;
+        }
+        if (!finished && launched >= maxit) {   // every iteration maxit allows is enqueued: drain
+            LS_CUDA_TRY(cudaEventSynchronize(h->ev[(nq - 1) & 1]));
+            finished = true;
+        }
+    }
+    k_final<K><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, x, info_dev ? info_dev : h->info);
+    LS_LAUNCH_CHECK();
+    if (info_host) {
+        LS_CUDA_TRY(cudaMemcpyAsync(info_host, info_dev ? info_dev : h->info, 8 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        LS_CUDA_TRY(cudaStreamSynchronize(stream));
+        const int st = (int)info_host[1];
+        if (st == 3) {
+            ls_set_error("CG breakdown after %d iterations (matrix not SPD or NaN in the right-hand side)", (int)info_host[0]);
+            return LS_ERR_BREAKDOWN;
+        }
+        if (st == 2) {
+            ls_set_error("PCG did not reach rtol=%g within maxit=%d (relres %g %g %g %g)", (double)rtol, maxit,
+                         (double)info_host[2], (double)info_host[3], (double)info_host[4], (double)info_host[5]);
+            return LS_ERR_NOT_CONVERGED;
+        }
+    }
+    return LS_OK;
+}
+
+}  // namespace
+
+extern "C" int ls_pcg_workspace_bytes(int64_t V, int64_t nnz, int k_max, size_t *bytes_out) {
+    LS_REQUIRE(bytes_out != nullptr, "bytes_out is NULL");
+    LS_REQUIRE(V > 0 && nnz > 0 && V < (int64_t)0x7ffffff0 && nnz < (int64_t)0x7ffffff0, "size out of range");
+    LS_REQUIRE(k_max >= 1 && k_max <= KMAX, "k_max must be in [1,4]");
+    *bytes_out = carve_handle(nullptr, nullptr, V, nnz, k_max, GRID_CAP);
+    return LS_OK;
+}
+
+extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const int32_t *rowptr, const int32_t *col,
+                             const float *val, int precond, int k_max, void *workspace, size_t workspace_bytes,
+                             void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LS_REQUIRE(handle_out != nullptr, "handle_out is NULL");
+    *handle_out = nullptr;
+    LS_REQUIRE(V > 0 && nnz > 0 && V < (int64_t)0x7ffffff0 && nnz < (int64_t)0x7ffffff0, "size out of range");
+    LS_REQUIRE(k_max >= 1 && k_max <= KMAX, "k_max must be in [1,4]");
+    LS_REQUIRE(precond == 0 || precond == 1, "precond must be 0 (none) or 1 (Jacobi)");
+    LS_REQUIRE(rowptr && col && val, "NULL CSR pointer");
+    LS_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 255) == 0, "workspace NULL or not 256-byte aligned");
+    LsDevInfo di;
+    int rc = ls_dev_info(&di);
+    if (rc) return rc;
+    size_t need = carve_handle(nullptr, nullptr, V, nnz, k_max, GRID_CAP);
+    if (workspace_bytes < need) {
+        ls_set_error("PCG workspace too small: %zu < %zu", workspace_bytes, need);
+        return LS_ERR_WORKSPACE;
+    }
+    PcgHandle *h = new (std::nothrow) PcgHandle();
+    LS_REQUIRE(h != nullptr, "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->V = V;
+    h->nnz = nnz;
+    h->k_max = k_max;
+    h->precond = precond;
+    h->device = di.device;
+    h->sm_count = di.sm_count;
+    h->ws_bytes = need;
+    carve_handle(h, (char *)workspace, V, nnz, k_max, GRID_CAP);
+
+    auto fail = [&](int code) {
+        ls_pcg_destroy(h);
+        return code;
+    };
+#define TRY_OR_FAIL(expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ls_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return fail(LS_ERR_CUDA);                                                          \
+        }                                                                                      \
+    } while (0)
+
+    TRY_OR_FAIL(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    TRY_OR_FAIL(cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming));
+    TRY_OR_FAIL(cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming));
+    TRY_OR_FAIL(cudaMallocHost((void **)&h->pinned_done, 64));
+
+    // zero the whole workspace once (padding of every plane must be 0), then copy the CSR in
+    TRY_OR_FAIL(cudaMemsetAsync(workspace, 0, need, stream));
+    TRY_OR_FAIL(cudaMemcpyAsync(h->rowptr, rowptr, (size_t)(V + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+    TRY_OR_FAIL(cudaMemcpyAsync(h->col, col, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, stream));
+    TRY_OR_FAIL(cudaMemcpyAsync(h->val, val, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, stream));
+    k_pad_tail<<<1, 32, 0, stream>>>(h->rowptr, h->col, h->val, V, nnz);
+    g_ls_launches.fetch_add(1);
+    TRY_OR_FAIL(cudaGetLastError());
+    k_dinv<<<(unsigned)((h->Vp + 255) / 256), 256, 0, stream>>>(V, h->Vp, h->rowptr, h->col, h->val, precond, h->dinv, h->flags);
+    g_ls_launches.fetch_add(1);
+    TRY_OR_FAIL(cudaGetLastError());
+
+    // launch geometry
+    lsk::spmm_config(&h->spmm_stages, &h->spmm_cap);
+    int occ = 1;
+    rc = lsk::spmm_prepare<3, true, true>(h->spmm_stages, h->spmm_cap, &occ);
+    if (rc) return fail(rc);
+    h->spmm_grid = lsk::spmm_grid_for(V, di.sm_count, occ);
+    if (h->spmm_grid > GRID_CAP) h->spmm_grid = GRID_CAP;
+    int vocc = 0;
+    TRY_OR_FAIL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vocc, k_update<3>, VEC_THREADS, 0));
+    if (vocc < 1) vocc = 1;
+    if (vocc > 8) vocc = 8;
+    int64_t vg = (h->Vp / 4 + VEC_THREADS - 1) / VEC_THREADS;
+    if (vg > (int64_t)di.sm_count * vocc) vg = (int64_t)di.sm_count * vocc;
+    if (vg < 1) vg = 1;
+    h->vec_grid = (int)vg;
+    k_partition<<<(h->spmm_grid + 1 + 127) / 128, 128, 0, stream>>>(V, h->rowptr, h->spmm_grid, h->part);
+    g_ls_launches.fetch_add(1);
+    TRY_OR_FAIL(cudaGetLastError());
+
+    int hflags = 0;
+    TRY_OR_FAIL(cudaMemcpyAsync(&hflags, h->flags, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    TRY_OR_FAIL(cudaStreamSynchronize(stream));
+    if (hflags & (1 | 4)) {
+        ls_set_error("CSR is malformed (column index out of range or decreasing rowptr)");
+        return fail(LS_ERR_INDEX_RANGE);
+    }
+    if (hflags & 2) {
+        ls_set_error("matrix has a missing or non-positive diagonal entry: not SPD");
+        return fail(LS_ERR_BREAKDOWN);
+    }
+#undef TRY_OR_FAIL
+    *handle_out = h;
+    return LS_OK;
+}
+
+extern "C" int ls_pcg_solve(void *handle, const float *b, float *x, const float *x0, int k, float rtol, int maxit,
+                            float *info_dev, float *info_host, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PcgHandle *h = (PcgHandle *)handle;
+    LS_REQUIRE(h != nullptr, "handle is NULL");
+    LS_REQUIRE(b != nullptr && x != nullptr, "b or x is NULL");
+    LS_REQUIRE(k >= 1 && k <= h->k_max, "k out of range for this handle");
+    LS_REQUIRE(rtol > 0.f && maxit > 0, "rtol and maxit must be positive");
+    int dev = -1;
+    LS_CUDA_TRY(cudaGetDevice(&dev));
+    LS_REQUIRE(dev == h->device, "handle was created on a different device");
+    switch (k) {
+        case 1: return solve_k<1>(h, b, x, x0, rtol, maxit, info_dev, info_host, stream);
+        case 2: return solve_k<2>(h, b, x, x0, rtol, maxit, info_dev, info_host, stream);
+        case 3: return solve_k<3>(h, b, x, x0, rtol, maxit, info_dev, info_host, stream);
+        default: return solve_k<4>(h, b, x, x0, rtol, maxit, info_dev, info_host, stream);
+    }
+}
+
+extern "C" int ls_pcg_destroy(void *handle) {
+    PcgHandle *h = (PcgHandle *)handle;
+    if (!h) return LS_OK;
+    for (int k = 0; k <= KMAX; ++k)
+        if (h->graph[k]) cudaGraphExecDestroy(h->graph[k]);
+    if (h->ev[0]) cudaEventDestroy(h->ev[0]);
+    if (h->ev[1]) cudaEventDestroy(h->ev[1]);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->pinned_done) cudaFreeHost(h->pinned_done);
+    delete h;
+    return LS_OK;
+}
+
+extern "C" int ls_pcg_bench_spmm(void *handle, int k, int launches, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PcgHandle *h = (PcgHandle *)handle;
+    LS_REQUIRE(h != nullptr, "handle is NULL");
+    LS_REQUIRE(k >= 1 && k <= h->k_max, "k out of range for this handle");
+    int occ, rc;
+    switch (k) {
+        case 1: rc = lsk::spmm_prepare<1, true, true>(h->spmm_stages, h->spmm_cap, &occ); break;
+        case 2: rc = lsk::spmm_prepare<2, true, true>(h->spmm_stages, h->spmm_cap, &occ); break;
+        case 3: rc = lsk::spmm_prepare<3, true, true>(h->spmm_stages, h->spmm_cap, &occ); break;
+        default: rc = lsk::spmm_prepare<4, true, true>(h->spmm_stages, h->spmm_cap, &occ); break;
+    }
+    if (rc) return rc;
+    for (int i = 0; i < launches; ++i) {
+        switch (k) {
+            case 1: rc = launch_spmm<1>(h, false, stream); break;
+            case 2: rc = launch_spmm<2>(h, false, stream); break;
+            case 3: rc = launch_spmm<3>(h, false, stream); break;
+            default: rc = launch_spmm<4>(h, false, stream); break;
+        }
+        if (rc) return rc;
+    }
+    return LS_OK;
+}
+
+extern "C" int64_t ls_pcg_spmm_bytes(void *handle, int k) {
+    PcgHandle *h = (PcgHandle *)handle;
+    if (!h) return 0;
+    return 8 * h->nnz + 4 * (h->V + 1) + 8 * (int64_t)k * h->V;
+}

@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library loads and exports every symbol include/largesteps_b200.h declares; host-only entry
+points validate their arguments without touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+import largesteps_b200._native as N
+
+HEADER = os.path.join(ROOT, "include", "largesteps_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ls_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_is_built_and_loads():
+    assert os.path.exists(N.LIB_PATH), "libls_b200.so missing: run __graft_entry__.build()"
+    lib = N.lib()
+    assert lib.ls_version() >= 100
+    assert isinstance(N.last_error(), str)
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = declared_symbols()
+    assert len(names) == len(N.SYMBOLS) >= 16
+    raw = ctypes.CDLL(N.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in the header but not exported"
+        assert n in N.SYMBOLS, f"{n} declared in the header but not bound in _native.SYMBOLS"
+    for n in N.SYMBOLS:
+        assert n in names, f"{n} bound in Python but not declared in the header"
+
+
+def test_status_strings():
+    lib = N.lib()
+    assert lib.ls_status_string(0) == b"ok"
+    for s in range(1, 8):
+        assert len(lib.ls_status_string(s)) > 0
+
+
+def test_host_side_argument_validation():
+    lib = N.lib()
+    nb = ctypes.c_size_t(0)
+    assert lib.ls_assemble_workspace_bytes(10, 8, ctypes.byref(nb)) == N.LS_OK and nb.value > 0
+    assert lib.ls_assemble_workspace_bytes(-1, 8, ctypes.byref(nb)) == N.LS_ERR_BAD_ARG
+    assert "negative" in N.last_error()
+    assert lib.ls_assemble_workspace_bytes(400_000_000, 8, ctypes.byref(nb)) == N.LS_ERR_BAD_ARG   # int32 bucket limit
+    assert lib.ls_pcg_workspace_bytes(1000, 7000, 3, ctypes.byref(nb)) == N.LS_OK
+    small = nb.value
+    assert lib.ls_pcg_workspace_bytes(1_000_000, 6_992_002, 4, ctypes.byref(nb)) == N.LS_OK
+    # 1M verts: CSR copy (60 MB) + 4x4 planes + dinv  ~ 0.33 GB
+    assert small < nb.value < 400e6
+    assert lib.ls_pcg_workspace_bytes(1000, 7000, 5, ctypes.byref(nb)) == N.LS_ERR_BAD_ARG
+    assert lib.ls_pcg_workspace_bytes(0, 0, 3, ctypes.byref(nb)) == N.LS_ERR_BAD_ARG
+    with pytest.raises(ValueError):
+        N.check(lib.ls_pcg_workspace_bytes(1000, 7000, 0, ctypes.byref(nb)))
+    assert lib.ls_pcg_destroy(None) == N.LS_OK
+    assert lib.ls_pcg_spmm_bytes(None, 3) == 0
+    assert lib.ls_launch_count() >= 0
+
+
+def test_check_maps_status_to_exceptions():
+    with pytest.raises(IndexError):
+        N.check(N.LS_ERR_INDEX_RANGE)
+    with pytest.raises(N.NotConverged):
+        N.check(N.LS_ERR_NOT_CONVERGED)
+    with pytest.raises(N.Breakdown):
+        N.check(N.LS_ERR_BREAKDOWN)
+    with pytest.raises(RuntimeError):
+        N.check(N.LS_ERR_CUDA)
+    N.check(N.LS_OK)

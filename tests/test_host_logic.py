@@ -1,0 +1,138 @@
+"""CPU: host-side logic of the operator surface (error behaviour, caches, sharding) -- no GPU compute."""
+import gc
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, PKG
+from largesteps_b200 import workloads, distributed
+from largesteps_b200 import geometry, parameterize, solvers, optimize
+
+
+def test_reference_import_names_resolve():
+    from largesteps.geometry import compute_matrix, laplacian_cot, laplacian_uniform          # noqa: F401
+    from largesteps.parameterize import to_differential, from_differential                    # noqa: F401
+    from largesteps.solvers import Solver, CholeskySolver, ConjugateGradientSolver, solve, DifferentiableSolve  # noqa: F401
+    from largesteps.optimize import AdamUniform                                                # noqa: F401
+    assert compute_matrix is geometry.compute_matrix
+    assert from_differential is parameterize.from_differential
+
+
+def test_alpha_validation_matches_reference(golden_assembly):
+    v = torch.zeros(4, 3)
+    f = torch.zeros(1, 3, dtype=torch.long)
+    for bad in (1.0, -0.1, 1.5):
+        with pytest.raises(ValueError) as e:
+            geometry.compute_matrix(v, f, 1.0, alpha=bad)
+        assert str(e.value).startswith(f"Invalid value for alpha: {bad}")
+    assert str(golden_assembly["alpha_error"]) == \
+        "Invalid value for alpha: 1.0 : it should take values between 0 (included) and 1 (excluded)"
+
+
+def test_no_cpu_fallback():
+    v = torch.zeros(4, 3)
+    f = torch.tensor([[0, 1, 2]])
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        geometry.compute_matrix(v, f, 1.0)
+    M = torch.sparse_coo_tensor(torch.tensor([[0, 1], [0, 1]]), torch.ones(2), (2, 2)).coalesce()
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        parameterize.from_differential(M, torch.zeros(2, 3))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        parameterize.to_differential(M, torch.zeros(2, 3))
+    p = torch.nn.Parameter(torch.zeros(3, 3))
+    p.grad = torch.zeros(3, 3)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        optimize.AdamUniform([p]).step()
+
+
+def test_unknown_method_message(golden_solve):
+    M = torch.sparse_coo_tensor(torch.tensor([[0, 1], [0, 1]]), torch.ones(2), (2, 2)).coalesce()
+    with pytest.raises(ValueError) as e:
+        parameterize.from_differential(M, torch.zeros(2, 3), method="nope")
+    assert str(e.value) == str(golden_solve["method_error"]) == "Unknown solver type 'nope'."
+
+
+def test_solver_base_class_contract():
+    with pytest.raises(NotImplementedError):
+        solvers.Solver(None).solve(torch.zeros(1, 1))
+
+
+def test_cache_is_weak_like_the_reference():
+    class Dummy:
+        pass
+    a = Dummy()
+    parameterize.cache_put(("k", "m"), "solver", a)
+    assert ("k", "m") in parameterize._cache
+    del a
+    gc.collect()
+    assert ("k", "m") not in parameterize._cache
+
+
+def test_workload_sizes_match_survey():
+    v, f = workloads.icosphere(4)
+    assert v.shape == (2562, 3) and f.shape == (5120, 3)
+    assert np.allclose(np.linalg.norm(v, axis=1), 1.0, atol=1e-6)
+    v, f = workloads.plane(100, seed=0)
+    assert v.shape == (10000, 3) and f.shape == (2 * 99 * 99, 3)
+    e = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1)
+    E = len(np.unique(e[:, 0] * 10000 + e[:, 1]))
+    assert 10000 + 2 * E == 7 * 100 * 100 - 8 * 100 + 2      # nnz(M) = 7n^2 - 8n + 2 (6992002 at n=1000)
+    assert 7 * 1000 * 1000 - 8 * 1000 + 2 == 6992002
+
+
+def test_bunny_subdivision_sizes(bunny_mesh):
+    v, f = bunny_mesh
+    assert v.shape == (3301, 3) and f.shape == (6598, 3)
+    v2, f2 = workloads.subdivide(*workloads.subdivide(v, f))
+    assert v2.shape[0] == 52786 and f2.shape[0] == 105568
+
+
+def test_assign_round_robin():
+    assert distributed.assign(8, 0, 1) == list(range(8))
+    assert distributed.assign(8, 1, 2) == [1, 3, 5, 7]
+    assert distributed.assign(8, 7, 8) == [7]
+    assert distributed.assign(3, 3, 4) == []
+    got = sorted(sum((distributed.assign(11, r, 4) for r in range(4)), []))
+    assert got == list(range(11))
+    with pytest.raises(ValueError):
+        distributed.assign(4, 2, 2)
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, PKG)
+    import torch.distributed as dist
+    import oracle
+    from largesteps_b200 import workloads as W, distributed as D
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        # two independent planes, one per rank (config 4 shape, tiny): each rank solves only its own mesh
+        mine = D.assign(world, rank, world)
+        assert mine == [rank]
+        v, f = W.plane(24, seed=rank)
+        r, c, val, V = oracle.compute_matrix(v, f, 1.0, alpha=0.95)
+        x = oracle.DirectSolver(r, c, val, V).solve(oracle.to_differential(r, c, val, V, v)).astype(np.float32)
+        allx = D.gather_solutions(torch.from_numpy(x))
+        assert allx.shape == (world, V, 3)
+        t = D.max_over_ranks(1.0 + rank)
+        n = D.sum_over_ranks(3)
+        D.barrier()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "gloo.npz"), allx=allx.numpy(), t=t, n=n)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    d = np.load(os.path.join(str(tmp_path), "gloo.npz"))
+    assert d["t"] == 2.0 and d["n"] == 6.0
+    # rank r's slot holds the solution of plane(seed=r): from_differential(to_differential(v)) == v
+    for r in range(2):
+        v, _ = workloads.plane(24, seed=r)
+        assert np.linalg.norm(d["allx"][r] - v) / np.linalg.norm(v) < 1e-5
