@@ -43,6 +43,7 @@ struct PcgCtrl {
     int done;        // 0 running, 1 converged, 2 maxit reached, 3 breakdown
     int conv[KMAX];  // column frozen
     int k;
+    int restart;     // warm start was worse than a cold start for some column: redo the initialisation from x = 0
 };
 
 struct PcgHandle {
@@ -188,8 +189,10 @@ struct VecArgs {
 
 // cold start: x = 0, r = b, p = z = dinv r;  warm (stage 2): r = b - Ap (Ap = A x0 from K1), p = z
 template <int K, bool WARM>
-__global__ void __launch_bounds__(VEC_THREADS) k_init(VecArgs a, const float *__restrict__ b, float rtol, int maxit) {
+__global__ void __launch_bounds__(VEC_THREADS) k_init(VecArgs a, const float *__restrict__ b, float rtol, int maxit,
+                                                      int only_if_restart) {
     __shared__ double red[3 * K * 32 + 3 * K + 1];
+    if (only_if_restart && *reinterpret_cast<volatile int *>(&a.ctrl->restart) == 0) return;
     double acc[3 * K];   // [rz | bb | rr]
 #pragma unroll
     for (int i = 0; i < 3 * K; ++i) acc[i] = 0.0;
@@ -214,9 +217,13 @@ __global__ void __launch_bounds__(VEC_THREADS) k_init(VecArgs a, const float *__
                                             blockIdx.x, gridDim.x);
     if (last && threadIdx.x == 0) {
         PcgCtrl *c = a.ctrl;
-        int all = 1;
+        int all = 1, worse = 0;
         const double rtol2 = (double)rtol * (double)rtol;
         for (int k = 0; k < K; ++k) {
+            // a warm start whose residual exceeds ||b|| is worse than x = 0 and, in fp32, caps the attainable
+            // accuracy at eps * kappa * ||x0|| / ||x||: fall back to the cold start (the reference CG has no such
+            // guard, solvers.py:107-110, and loses accuracy when the gradient scale changes between steps)
+            if (WARM && tot[2 * K + k] > tot[K + k]) worse = 1;
             c->rz[k] = tot[k];
             c->rz_new[k] = tot[k];
             c->bb[k] = tot[K + k];
@@ -236,7 +243,8 @@ __global__ void __launch_bounds__(VEC_THREADS) k_init(VecArgs a, const float *__
         c->maxit = maxit;
         c->it = 0;
         c->k = K;
-        c->done = all ? 1 : 0;
+        c->restart = worse;
+        c->done = (all && !worse) ? 1 : 0;
     }
 }
 
@@ -465,10 +473,12 @@ int solve_k(PcgHandle *h, const float *b, float *x, const float *x0, float rtol,
         LS_LAUNCH_CHECK();
         rc = launch_spmm<K>(h, false, stream);
         if (rc) return rc;
-        k_init<K, true><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, b, rtol, maxit);
+        k_init<K, true><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, b, rtol, maxit, 0);
+        LS_LAUNCH_CHECK();
+        k_init<K, false><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, b, rtol, maxit, 1);   // runs only if `restart`
         LS_LAUNCH_CHECK();
     } else {
-        k_init<K, false><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, b, rtol, maxit);
+        k_init<K, false><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, b, rtol, maxit, 0);
         LS_LAUNCH_CHECK();
     }
     // iterate: replay the CHUNK-iteration graph; the device `done` flag of chunk c-1 is checked while chunk c runs

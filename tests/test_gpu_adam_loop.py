@@ -44,7 +44,8 @@ def test_adam_uniform_large_and_param_groups():
 
 def test_tutorial_shaped_loop_tracks_cpu_oracle():
     """Stand-in for suzanne->target (scenes and nvdiffrast are not available): source icosphere, target = displaced
-    sphere with the same connectivity, loss = mean |v - v_target| (L1, like the image loss of scripts/main.py:186)."""
+    sphere with the same connectivity, loss = mean (v - v_target)^2 (the L2 image loss option of scripts/main.py:188;
+    smooth, so the GPU and CPU trajectories can be compared step by step)."""
     v, f = workloads.icosphere(3)
     V = len(v)
     target = (v * (1.0 + 0.3 * np.sin(3 * v[:, :1]) * np.cos(2 * v[:, 1:2]))).astype(np.float32)
@@ -62,14 +63,14 @@ def test_tutorial_shaped_loop_tracks_cpu_oracle():
     losses = []
     for step in range(200):
         x = from_differential(M, u, "Cholesky")
-        loss = (x - tgt).abs().mean()
+        loss = ((x - tgt) ** 2).mean()
         opt.zero_grad()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
-        if step < 5:      # trajectories agree while sign(x - target) is stable
+        losses.append(float(loss.detach()))
+        if step < 5:
             xo = ds.solve(uo)
-            go = ds.solve(np.sign(xo - target) / (3 * V))
+            go = ds.solve(2.0 * (xo - target) / (3 * V))
             uo = oo.step(uo, go.astype(np.float32))
             assert rel_l2(u.detach().cpu().numpy(), uo) < 1e-4, step
-    assert losses[-1] < 0.15 * losses[0]
+    assert losses[-1] < 0.05 * losses[0]
