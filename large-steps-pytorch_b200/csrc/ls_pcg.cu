@@ -265,11 +265,29 @@ __global__ void __launch_bounds__(VEC_THREADS) k_warm_load(VecArgs a, const floa
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
-// K2: x += alpha p, r -= alpha Ap, rz' = r.(dinv r), rr = r.r ; last CTA: scalar state transition
+// K2: x += alpha p, r -= alpha Ap, rz' = r.(dinv r), rr = r.r ; last CTA: scalar state transition.
+// One float4 per thread per column (grid sized to cover the planes in one pass when it fits); the vector loads are
+// issued BEFORE the dependent scalar chain (done flag -> pAp/rz -> fp64 divide) so that chain hides under them.
 template <int K>
-__global__ void __launch_bounds__(VEC_THREADS) k_update(VecArgs a) {
+__global__ void __launch_bounds__(VEC_THREADS, 2) k_update(VecArgs a) {
     __shared__ double red[2 * K * 32 + 2 * K + 1];
     PcgCtrl *c = a.ctrl;
+    const int64_t n4 = a.Vp >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 d, xv[K], pv[K], rv[K], qv[K];
+    auto load = [&](int64_t j) {
+        d = ld4(a.dinv + 4 * j);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const size_t o = (size_t)k * a.Vp + 4 * j;
+            xv[k] = ld4(a.x + o);
+            pv[k] = ld4(a.p + o);
+            rv[k] = ld4(a.r + o);
+            qv[k] = ld4(a.Ap + o);
+        }
+    };
+    if (i < n4) load(i);
     if (*reinterpret_cast<volatile int *>(&c->done) != 0) return;
     float alpha[K];
 #pragma unroll
@@ -279,19 +297,9 @@ __global__ void __launch_bounds__(VEC_THREADS) k_update(VecArgs a) {
     }
     double acc[2 * K];
 #pragma unroll
-    for (int i = 0; i < 2 * K; ++i) acc[i] = 0.0;
-    const int64_t n4 = a.Vp >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 d = ld4(a.dinv + 4 * i);
-        float4 xv[K], pv[K], rv[K], qv[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const size_t o = (size_t)k * a.Vp + 4 * i;
-            xv[k] = ld4(a.x + o);
-            pv[k] = ld4(a.p + o);
-            rv[k] = ld4(a.r + o);
-            qv[k] = ld4(a.Ap + o);
-        }
+    for (int q = 0; q < 2 * K; ++q) acc[q] = 0.0;
+    for (bool first = true; i < n4; i += stride, first = false) {
+        if (!first) load(i);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const size_t o = (size_t)k * a.Vp + 4 * i;
@@ -338,24 +346,30 @@ __global__ void __launch_bounds__(VEC_THREADS) k_update(VecArgs a) {
     }
 }
 
-// K3: p = dinv r + beta p
+// K3: p = dinv r + beta p   (same loads-first structure as K2)
 template <int K>
-__global__ void __launch_bounds__(VEC_THREADS) k_pupdate(VecArgs a) {
+__global__ void __launch_bounds__(VEC_THREADS, 4) k_pupdate(VecArgs a) {
     PcgCtrl *c = a.ctrl;
+    const int64_t n4 = a.Vp >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 d, pv[K], rv[K];
+    auto load = [&](int64_t j) {
+        d = ld4(a.dinv + 4 * j);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const size_t o = (size_t)k * a.Vp + 4 * j;
+            pv[k] = ld4(a.p + o);
+            rv[k] = ld4(a.r + o);
+        }
+    };
+    if (i < n4) load(i);
     if (*reinterpret_cast<volatile int *>(&c->done) != 0) return;
     float beta[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) beta[k] = c->beta[k];
-    const int64_t n4 = a.Vp >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 d = ld4(a.dinv + 4 * i);
-        float4 pv[K], rv[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const size_t o = (size_t)k * a.Vp + 4 * i;
-            pv[k] = ld4(a.p + o);
-            rv[k] = ld4(a.r + o);
-        }
+    for (bool first = true; i < n4; i += stride, first = false) {
+        if (!first) load(i);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const size_t o = (size_t)k * a.Vp + 4 * i;
@@ -598,12 +612,8 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
     if (rc) return fail(rc);
     h->spmm_grid = lsk::spmm_grid_for(V, di.sm_count, occ);
     if (h->spmm_grid > GRID_CAP) h->spmm_grid = GRID_CAP;
-    int vocc = 0;
-    TRY_OR_FAIL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vocc, k_update<3>, VEC_THREADS, 0));
-    if (vocc < 1) vocc = 1;
-    if (vocc > 8) vocc = 8;
-    int64_t vg = (h->Vp / 4 + VEC_THREADS - 1) / VEC_THREADS;
-    if (vg > (int64_t)di.sm_count * vocc) vg = (int64_t)di.sm_count * vocc;
+    int64_t vg = (h->Vp / 4 + VEC_THREADS - 1) / VEC_THREADS;   // one float4 per thread per column
+    if (vg > GRID_CAP) vg = GRID_CAP;                           // beyond that the kernels grid-stride
     if (vg < 1) vg = 1;
     h->vec_grid = (int)vg;
     k_partition<<<(h->spmm_grid + 1 + 127) / 128, 128, 0, stream>>>(V, h->rowptr, h->spmm_grid, h->part);
