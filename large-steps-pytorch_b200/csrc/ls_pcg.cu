@@ -19,14 +19,8 @@
 // The iteration loop is a CUDA graph of CHUNK iterations replayed until the device-side `done` flag is seen.
 #include <new>
 #include <string.h>
-#include "ls_spmm_kernel.cuh"
-
-namespace lsk {
-void spmm_config(int *stages, int *cap);
-template <int K, bool SOA, bool DOT> int spmm_prepare(int stages, int cap, int *ctas_per_sm);
-template <int K, bool SOA, bool DOT> int spmm_launch(const SpmmArgs &a, int grid, cudaStream_t stream);
-int spmm_grid_for(int64_t V, int sm_count, int occ);
-}  // namespace lsk
+#include <stdlib.h>
+#include "ls_spmm_host.h"
 
 namespace {
 
@@ -62,8 +56,13 @@ struct PcgHandle {
     float *info;
     int *flags;
     // launch geometry
-    int spmm_stages, spmm_cap, spmm_grid;
+    lsk::SpmmCfg cfg;
+    int spmm_grid;
     int vec_grid;
+    int4 *desc;
+    int *desc_cnt;
+    int planned;
+    int vec_mode;
     // graphs, one per K
     cudaGraphExec_t graph[KMAX + 1];
     cudaStream_t cap_stream;
@@ -93,6 +92,8 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
     size_t o_p = c.take((size_t)Vp * 4 * k_max);
     size_t o_Ap = c.take((size_t)Vp * 4 * k_max);
     size_t o_part = c.take((size_t)(grid_cap + 1) * 4);
+    size_t o_desc = c.take((size_t)grid_cap * lsk::SPMM_BMAX * sizeof(int4));
+    size_t o_dcnt = c.take((size_t)grid_cap * 4);
     size_t o_ctrl = c.take(sizeof(PcgCtrl));
     size_t o_ps = c.take((size_t)grid_cap * KMAX * 8);
     size_t o_pv = c.take((size_t)grid_cap * 3 * KMAX * 8);
@@ -110,6 +111,8 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
         h->p = (float *)(base + o_p);
         h->Ap = (float *)(base + o_Ap);
         h->part = (int *)(base + o_part);
+        h->desc = (int4 *)(base + o_desc);
+        h->desc_cnt = (int *)(base + o_dcnt);
         h->ctrl = (PcgCtrl *)(base + o_ctrl);
         h->part_spmm = (double *)(base + o_ps);
         h->part_vec = (double *)(base + o_pv);
@@ -265,6 +268,31 @@ __global__ void __launch_bounds__(VEC_THREADS) k_warm_load(VecArgs a, const floa
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
+// scalar state transition run by the last CTA of K2: beta, per-column convergence, iteration count, done flag
+template <int K>
+__device__ __forceinline__ void pcg_transition(PcgCtrl *c, const double (&tot)[2 * K]) {
+    int all = 1, bad = 0;
+    for (int k = 0; k < K; ++k) {
+        if (c->conv[k]) continue;
+        const double pAp = c->pAp[k];
+        if (!(pAp > 0.0) || !(tot[k] == tot[k])) bad = 1;   // not SPD, or NaN crept in
+        const double rz_old = c->rz[k];
+        c->beta[k] = (rz_old > 0.0) ? (float)(tot[k] / rz_old) : 0.f;
+        c->rz[k] = tot[k];
+        c->rz_new[k] = tot[k];
+        c->rr[k] = tot[K + k];
+        const int cv = tot[K + k] <= (double)c->rtol2 * c->bb[k];
+        c->conv[k] = cv;
+        if (cv) c->beta[k] = 0.f;
+        all &= cv;
+    }
+    const int it = c->it + 1;
+    c->it = it;
+    if (bad) c->done = 3;
+    else if (all) c->done = 1;
+    else if (it >= c->maxit) c->done = 2;
+}
+
 // K2: x += alpha p, r -= alpha Ap, rz' = r.(dinv r), rr = r.r ; last CTA: scalar state transition.
 // One float4 per thread per column (grid sized to cover the planes in one pass when it fits); the vector loads are
 // issued BEFORE the dependent scalar chain (done flag -> pAp/rz -> fp64 divide) so that chain hides under them.
@@ -322,28 +350,7 @@ __global__ void __launch_bounds__(VEC_THREADS, 2) k_update(VecArgs a) {
     double tot[2 * K];
     const bool last = ls_grid_reduce<2 * K>(acc, tot, a.partials, a.ticket, red, threadIdx.x, VEC_THREADS, 1,
                                             blockIdx.x, gridDim.x);
-    if (last && threadIdx.x == 0) {
-        int all = 1, bad = 0;
-        for (int k = 0; k < K; ++k) {
-            if (c->conv[k]) continue;
-            const double pAp = c->pAp[k];
-            if (!(pAp > 0.0) || !(tot[k] == tot[k])) bad = 1;   // not SPD, or NaN crept in
-            const double rz_old = c->rz[k];
-            c->beta[k] = (rz_old > 0.0) ? (float)(tot[k] / rz_old) : 0.f;
-            c->rz[k] = tot[k];
-            c->rz_new[k] = tot[k];
-            c->rr[k] = tot[K + k];
-            const int cv = tot[K + k] <= (double)c->rtol2 * c->bb[k];
-            c->conv[k] = cv;
-            if (cv) c->beta[k] = 0.f;
-            all &= cv;
-        }
-        const int it = c->it + 1;
-        c->it = it;
-        if (bad) c->done = 3;
-        else if (all) c->done = 1;
-        else if (it >= c->maxit) c->done = 2;
-    }
+    if (last && threadIdx.x == 0) pcg_transition<K>(c, tot);
 }
 
 // K3: p = dinv r + beta p   (same loads-first structure as K2)
@@ -383,6 +390,61 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_pupdate(VecArgs a) {
     }
 }
 
+// Column-serial variants of K2 / K3: one column at a time per thread (4-5 float4 loads in flight instead of 13),
+// ~40 registers -> full occupancy.  Selected with LS_VEC_MODE=1 (sweeps); same arithmetic, same reduction order
+// per column, so results are bitwise identical to the fused-column variants.
+template <int K>
+__global__ void __launch_bounds__(VEC_THREADS, 4) k_update_cs(VecArgs a) {
+    __shared__ double red[2 * K * 32 + 2 * K + 1];
+    PcgCtrl *c = a.ctrl;
+    const int64_t n4 = a.Vp >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f), x0, p0, r0, q0;
+    if (i0 < n4) {
+        d = ld4(a.dinv + 4 * i0);
+        x0 = ld4(a.x + 4 * i0);
+        p0 = ld4(a.p + 4 * i0);
+        r0 = ld4(a.r + 4 * i0);
+        q0 = ld4(a.Ap + 4 * i0);
+    }
+    if (*reinterpret_cast<volatile int *>(&c->done) != 0) return;
+    float alpha[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double pAp = c->pAp[k];
+        alpha[k] = (c->conv[k] || !(pAp > 0.0)) ? 0.f : (float)(c->rz[k] / pAp);
+    }
+    double acc[2 * K];
+#pragma unroll
+    for (int q = 0; q < 2 * K; ++q) acc[q] = 0.0;
+    for (int64_t i = i0; i < n4; i += stride) {
+        if (i != i0) d = ld4(a.dinv + 4 * i);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const size_t o = (size_t)k * a.Vp + 4 * i;
+            float4 xv, pv, rv, qv;
+            if (k == 0 && i == i0) {
+                xv = x0; pv = p0; rv = r0; qv = q0;
+            } else {
+                xv = ld4(a.x + o); pv = ld4(a.p + o); rv = ld4(a.r + o); qv = ld4(a.Ap + o);
+            }
+            const float al = alpha[k];
+            xv.x = fmaf(al, pv.x, xv.x); xv.y = fmaf(al, pv.y, xv.y); xv.z = fmaf(al, pv.z, xv.z); xv.w = fmaf(al, pv.w, xv.w);
+            rv.x = fmaf(-al, qv.x, rv.x); rv.y = fmaf(-al, qv.y, rv.y); rv.z = fmaf(-al, qv.z, rv.z); rv.w = fmaf(-al, qv.w, rv.w);
+            st4(a.x + o, xv);
+            st4(a.r + o, rv);
+            const float r2x = rv.x * rv.x, r2y = rv.y * rv.y, r2z = rv.z * rv.z, r2w = rv.w * rv.w;
+            acc[k] += (double)(d.x * r2x) + (double)(d.y * r2y) + (double)(d.z * r2z) + (double)(d.w * r2w);
+            acc[K + k] += (double)r2x + (double)r2y + (double)r2z + (double)r2w;
+        }
+    }
+    double tot[2 * K];
+    const bool last = ls_grid_reduce<2 * K>(acc, tot, a.partials, a.ticket, red, threadIdx.x, VEC_THREADS, 1,
+                                            blockIdx.x, gridDim.x);
+    if (last && threadIdx.x == 0) pcg_transition<K>(c, tot);
+}
+
 // x (SoA) -> out (AoS), info
 template <int K>
 __global__ void __launch_bounds__(VEC_THREADS) k_final(VecArgs a, float *__restrict__ out, float *__restrict__ info) {
@@ -420,8 +482,11 @@ VecArgs vec_args(PcgHandle *h, int which_ticket) {
 lsk::SpmmArgs spmm_args(PcgHandle *h, bool with_done) {
     lsk::SpmmArgs s{};
     s.V = (int)h->V;
-    s.stages = h->spmm_stages;
-    s.cap = h->spmm_cap;
+    s.stages = h->cfg.stages;
+    s.cap = h->cfg.cap;
+    s.hint = h->cfg.hint;
+    s.desc = h->planned ? h->desc : nullptr;
+    s.desc_cnt = h->desc_cnt;
     s.rowptr = h->rowptr;
     s.col = h->col;
     s.val = h->val;
@@ -439,14 +504,15 @@ lsk::SpmmArgs spmm_args(PcgHandle *h, bool with_done) {
 
 template <int K>
 int launch_spmm(PcgHandle *h, bool with_done, cudaStream_t s) {
-    return lsk::spmm_launch<K, true, true>(spmm_args(h, with_done), h->spmm_grid, s);
+    return lsk::spmm_launch(K, true, h->cfg, spmm_args(h, with_done), h->spmm_grid, s);
 }
 
 template <int K>
 int launch_iteration(PcgHandle *h, cudaStream_t s) {
     int rc = launch_spmm<K>(h, true, s);
     if (rc) return rc;
-    k_update<K><<<h->vec_grid, VEC_THREADS, 0, s>>>(vec_args(h, 1));
+    if (h->vec_mode == 1) k_update_cs<K><<<h->vec_grid, VEC_THREADS, 0, s>>>(vec_args(h, 1));
+    else k_update<K><<<h->vec_grid, VEC_THREADS, 0, s>>>(vec_args(h, 1));
     LS_LAUNCH_CHECK();
     k_pupdate<K><<<h->vec_grid, VEC_THREADS, 0, s>>>(vec_args(h, 1));
     LS_LAUNCH_CHECK();
@@ -477,7 +543,7 @@ template <int K>
 int solve_k(PcgHandle *h, const float *b, float *x, const float *x0, float rtol, int maxit, float *info_dev,
             float *info_host, cudaStream_t stream) {
     int occ;
-    int rc = lsk::spmm_prepare<K, true, true>(h->spmm_stages, h->spmm_cap, &occ);
+    int rc = lsk::spmm_prepare(K, true, h->cfg, &occ);
     if (rc) return rc;
     rc = build_graph<K>(h);
     if (rc) return rc;
@@ -606,9 +672,13 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
     TRY_OR_FAIL(cudaGetLastError());
 
     // launch geometry
-    lsk::spmm_config(&h->spmm_stages, &h->spmm_cap);
+    lsk::spmm_config(&h->cfg);
+    {
+        const char *e = getenv("LS_VEC_MODE");
+        h->vec_mode = e ? atoi(e) : 1;
+    }
     int occ = 1;
-    rc = lsk::spmm_prepare<3, true, true>(h->spmm_stages, h->spmm_cap, &occ);
+    rc = lsk::spmm_prepare(3, true, h->cfg, &occ);
     if (rc) return fail(rc);
     h->spmm_grid = lsk::spmm_grid_for(V, di.sm_count, occ);
     if (h->spmm_grid > GRID_CAP) h->spmm_grid = GRID_CAP;
@@ -620,9 +690,15 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
     g_ls_launches.fetch_add(1);
     TRY_OR_FAIL(cudaGetLastError());
 
-    int hflags = 0;
-    TRY_OR_FAIL(cudaMemcpyAsync(&hflags, h->flags, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    // block plan: every CTA's block boundaries, so the producer warp never chases rowptr at run time
+    rc = lsk::spmm_plan(h->rowptr, h->part, h->spmm_grid, h->cfg.cap, h->desc, h->desc_cnt, h->flags + 1, stream);
+    if (rc) return fail(rc);
+
+    int hflags2[2] = {0, 0};
+    TRY_OR_FAIL(cudaMemcpyAsync(hflags2, h->flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     TRY_OR_FAIL(cudaStreamSynchronize(stream));
+    const int hflags = hflags2[0];
+    h->planned = (hflags2[1] == 0) ? 1 : 0;
     if (hflags & (1 | 4)) {
         ls_set_error("CSR is malformed (column index out of range or decreasing rowptr)");
         return fail(LS_ERR_INDEX_RANGE);
@@ -673,21 +749,11 @@ extern "C" int ls_pcg_bench_spmm(void *handle, int k, int launches, void *stream
     PcgHandle *h = (PcgHandle *)handle;
     LS_REQUIRE(h != nullptr, "handle is NULL");
     LS_REQUIRE(k >= 1 && k <= h->k_max, "k out of range for this handle");
-    int occ, rc;
-    switch (k) {
-        case 1: rc = lsk::spmm_prepare<1, true, true>(h->spmm_stages, h->spmm_cap, &occ); break;
-        case 2: rc = lsk::spmm_prepare<2, true, true>(h->spmm_stages, h->spmm_cap, &occ); break;
-        case 3: rc = lsk::spmm_prepare<3, true, true>(h->spmm_stages, h->spmm_cap, &occ); break;
-        default: rc = lsk::spmm_prepare<4, true, true>(h->spmm_stages, h->spmm_cap, &occ); break;
-    }
+    int occ;
+    int rc = lsk::spmm_prepare(k, true, h->cfg, &occ);
     if (rc) return rc;
     for (int i = 0; i < launches; ++i) {
-        switch (k) {
-            case 1: rc = launch_spmm<1>(h, false, stream); break;
-            case 2: rc = launch_spmm<2>(h, false, stream); break;
-            case 3: rc = launch_spmm<3>(h, false, stream); break;
-            default: rc = launch_spmm<4>(h, false, stream); break;
-        }
+        rc = lsk::spmm_launch(k, true, h->cfg, spmm_args(h, false), h->spmm_grid, stream);
         if (rc) return rc;
     }
     return LS_OK;

@@ -1,60 +1,91 @@
-// ls_spmm.cu -- public y = A x entry point (AoS (V,k) torch layout) on top of the TMA-staged SpMM kernel.
+// ls_spmm.cu -- SpMM launch plumbing + the public y = A x entry point (AoS (V,k) torch layout).
 // Replaces the torch sparse `M @ v` of parameterize.py:30 (to_differential) and scripts/main.py:192-195.
 #include <stdlib.h>
 #include "ls_spmm_kernel.cuh"
+#include "ls_spmm_host.h"
 
 namespace lsk {
 
-// runtime tuning knobs (defaults chosen on B200; override with LS_SPMM_STAGES / LS_SPMM_CAPMUL for sweeps)
-void spmm_config(int *stages, int *cap) {
-    static int s_stages = 0, s_cap = 0;
-    if (s_stages == 0) {
-        const char *e1 = getenv("LS_SPMM_STAGES");
-        const char *e2 = getenv("LS_SPMM_CAPMUL");
-        int st = e1 ? atoi(e1) : 2;
-        int cm = e2 ? atoi(e2) : 10;
-        if (st < 2) st = 2;
-        if (st > SPMM_MAX_STAGES) st = SPMM_MAX_STAGES;
-        if (cm < 2) cm = 2;
-        if (cm > 24) cm = 24;
-        s_stages = st;
-        s_cap = SPMM_NT * cm;
+// runtime tuning knobs (defaults chosen on B200; LS_SPMM_* environment variables exist for sweeps only)
+void spmm_config(SpmmCfg *cfg) {
+    static SpmmCfg s = {0, 0, 0, 0};
+    if (s.stages == 0) {
+        auto geti = [](const char *name, int dflt, int lo, int hi) {
+            const char *e = getenv(name);
+            int v = e ? atoi(e) : dflt;
+            return v < lo ? lo : (v > hi ? hi : v);
+        };
+        s.stages = geti("LS_SPMM_STAGES", 2, 2, SPMM_MAX_STAGES);
+        s.cap = SPMM_NT * geti("LS_SPMM_CAPMUL", 8, 2, 24);
+        s.unroll = geti("LS_SPMM_UNROLL", 8, 4, 8) >= 8 ? 8 : 4;
+        s.hint = geti("LS_SPMM_HINT", 1, 0, 2);   // in-solver matrix stream: L2 evict_first
     }
-    *stages = s_stages;
-    *cap = s_cap;
+    *cfg = s;
 }
 
-template <int K, bool SOA, bool DOT>
-int spmm_prepare(int stages, int cap, int *ctas_per_sm) {
+namespace {
+template <int K, bool SOA, bool DOT, int U>
+int prepare_t(const SpmmCfg &cfg, int *ctas_per_sm) {
     static thread_local int cached_dev = -1, cached_occ = 0, cached_st = 0, cached_cap = 0;
     LsDevInfo di;
     int rc = ls_dev_info(&di);
     if (rc) return rc;
-    if (cached_dev != di.device || cached_st != stages || cached_cap != cap) {
-        size_t smem = spmm_smem_bytes(stages, cap);
+    if (cached_dev != di.device || cached_st != cfg.stages || cached_cap != cfg.cap) {
+        size_t smem = spmm_smem_bytes(cfg.stages, cfg.cap);
         if ((int)smem > di.max_smem_optin) {
             ls_set_error("SpMM stage configuration needs %zu bytes of shared memory, device allows %d", smem, di.max_smem_optin);
             return LS_ERR_UNSUPPORTED;
         }
-        LS_CUDA_TRY(cudaFuncSetAttribute(spmm_tma_kernel<K, SOA, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LS_CUDA_TRY(cudaFuncSetAttribute(spmm_tma_kernel<K, SOA, DOT, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        LS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_tma_kernel<K, SOA, DOT>, SPMM_THREADS, smem));
+        LS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_tma_kernel<K, SOA, DOT, U>, SPMM_THREADS, smem));
         if (occ < 1) occ = 1;
         cached_dev = di.device;
         cached_occ = occ;
-        cached_st = stages;
-        cached_cap = cap;
+        cached_st = cfg.stages;
+        cached_cap = cfg.cap;
     }
     *ctas_per_sm = cached_occ;
     return LS_OK;
 }
 
-template <int K, bool SOA, bool DOT>
-int spmm_launch(const SpmmArgs &a, int grid, cudaStream_t stream) {
+template <int K, bool SOA, bool DOT, int U>
+int launch_t(const SpmmArgs &a, int grid, cudaStream_t stream) {
     size_t smem = spmm_smem_bytes(a.stages, a.cap);
-    spmm_tma_kernel<K, SOA, DOT><<<grid, SPMM_THREADS, smem, stream>>>(a);
+    spmm_tma_kernel<K, SOA, DOT, U><<<grid, SPMM_THREADS, smem, stream>>>(a);
     LS_LAUNCH_CHECK();
     return LS_OK;
+}
+}  // namespace
+
+#define LS_SPMM_DISPATCH(FN, ...)                                                                         \
+    do {                                                                                                  \
+        const bool u8 = cfg.unroll >= 8;                                                                  \
+        if (solver_layout) {                                                                              \
+            switch (K) {                                                                                  \
+                case 1: return u8 ? FN<1, true, true, 8>(__VA_ARGS__) : FN<1, true, true, 4>(__VA_ARGS__); \
+                case 2: return u8 ? FN<2, true, true, 8>(__VA_ARGS__) : FN<2, true, true, 4>(__VA_ARGS__); \
+                case 3: return u8 ? FN<3, true, true, 8>(__VA_ARGS__) : FN<3, true, true, 4>(__VA_ARGS__); \
+                case 4: return u8 ? FN<4, true, true, 8>(__VA_ARGS__) : FN<4, true, true, 4>(__VA_ARGS__); \
+            }                                                                                             \
+        } else {                                                                                          \
+            switch (K) {                                                                                  \
+                case 1: return u8 ? FN<1, false, false, 8>(__VA_ARGS__) : FN<1, false, false, 4>(__VA_ARGS__); \
+                case 2: return u8 ? FN<2, false, false, 8>(__VA_ARGS__) : FN<2, false, false, 4>(__VA_ARGS__); \
+                case 3: return u8 ? FN<3, false, false, 8>(__VA_ARGS__) : FN<3, false, false, 4>(__VA_ARGS__); \
+                case 4: return u8 ? FN<4, false, false, 8>(__VA_ARGS__) : FN<4, false, false, 4>(__VA_ARGS__); \
+            }                                                                                             \
+        }                                                                                                 \
+        ls_set_error("SpMM: k=%d out of range [1,4]", K);                                                 \
+        return LS_ERR_BAD_ARG;                                                                            \
+    } while (0)
+
+int spmm_prepare(int K, bool solver_layout, const SpmmCfg &cfg, int *ctas_per_sm) {
+    LS_SPMM_DISPATCH(prepare_t, cfg, ctas_per_sm);
+}
+
+int spmm_launch(int K, bool solver_layout, const SpmmCfg &cfg, const SpmmArgs &a, int grid, cudaStream_t stream) {
+    LS_SPMM_DISPATCH(launch_t, a, grid, stream);
 }
 
 int spmm_grid_for(int64_t V, int sm_count, int occ) {
@@ -65,15 +96,12 @@ int spmm_grid_for(int64_t V, int sm_count, int occ) {
     return (int)g;
 }
 
-// explicit instantiations used by ls_pcg.cu
-template int spmm_prepare<1, true, true>(int, int, int *);
-template int spmm_prepare<2, true, true>(int, int, int *);
-template int spmm_prepare<3, true, true>(int, int, int *);
-template int spmm_prepare<4, true, true>(int, int, int *);
-template int spmm_launch<1, true, true>(const SpmmArgs &, int, cudaStream_t);
-template int spmm_launch<2, true, true>(const SpmmArgs &, int, cudaStream_t);
-template int spmm_launch<3, true, true>(const SpmmArgs &, int, cudaStream_t);
-template int spmm_launch<4, true, true>(const SpmmArgs &, int, cudaStream_t);
+int spmm_plan(const int *rowptr, const int *part, int G, int cap, int4 *desc, int *desc_cnt, int *overflow,
+              cudaStream_t stream) {
+    spmm_plan_kernel<<<(G + 127) / 128, 128, 0, stream>>>(rowptr, part, G, cap, desc, desc_cnt, overflow);
+    LS_LAUNCH_CHECK();
+    return LS_OK;
+}
 
 }  // namespace lsk
 
@@ -91,14 +119,15 @@ extern "C" int ls_spmm_csr_f32(int64_t V, const int32_t *rowptr, const int32_t *
     LsDevInfo di;
     int rc = ls_dev_info(&di);
     if (rc) return rc;
-    int stages, cap;
-    spmm_config(&stages, &cap);
+    SpmmCfg cfg;
+    spmm_config(&cfg);
     for (int k0 = 0; k0 < k; k0 += 4) {
-        int kk = (k - k0) < 4 ? (k - k0) : 4;
+        const int kk = (k - k0) < 4 ? (k - k0) : 4;
         SpmmArgs a{};
         a.V = (int)V;
-        a.stages = stages;
-        a.cap = cap;
+        a.stages = cfg.stages;
+        a.cap = cfg.cap;
+        a.hint = 0;
         a.rowptr = rowptr;
         a.col = col;
         a.val = val;
@@ -107,20 +136,9 @@ extern "C" int ls_spmm_csr_f32(int64_t V, const int32_t *rowptr, const int32_t *
         a.ldx = ldx;
         a.ldy = ldy;
         int occ = 1;
-        switch (kk) {
-            case 1: rc = spmm_prepare<1, false, false>(stages, cap, &occ); break;
-            case 2: rc = spmm_prepare<2, false, false>(stages, cap, &occ); break;
-            case 3: rc = spmm_prepare<3, false, false>(stages, cap, &occ); break;
-            default: rc = spmm_prepare<4, false, false>(stages, cap, &occ); break;
-        }
+        rc = spmm_prepare(kk, false, cfg, &occ);
         if (rc) return rc;
-        int grid = spmm_grid_for(V, di.sm_count, occ);
-        switch (kk) {
-            case 1: rc = spmm_launch<1, false, false>(a, grid, stream); break;
-            case 2: rc = spmm_launch<2, false, false>(a, grid, stream); break;
-            case 3: rc = spmm_launch<3, false, false>(a, grid, stream); break;
-            default: rc = spmm_launch<4, false, false>(a, grid, stream); break;
-        }
+        rc = spmm_launch(kk, false, cfg, a, spmm_grid_for(V, di.sm_count, occ), stream);
         if (rc) return rc;
     }
     return LS_OK;

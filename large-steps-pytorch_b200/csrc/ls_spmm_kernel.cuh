@@ -6,7 +6,8 @@
 //   * persistent CTAs, each owning a contiguous, nnz-balanced range of rows (`part`);
 //   * a producer warp streams, per block of <= NT rows, the *contiguous* col/val/rowptr slices of that block into a
 //     shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx) -- 2/3 of all bytes of the
-//     kernel never touch the LSU or the register file on their way in;
+//     kernel never touch the LSU or the register file on their way in.  With a plan (`desc`, built once per matrix)
+//     the producer knows every block boundary up front and issues the first copies one L2 round trip after launch;
 //   * NT consumer threads take one row each out of shared memory (odd stride -> conflict-free), gather x through
 //     L1 (neighbouring rows share neighbours, so the gather is mostly L1/L2 hits), and write y coalesced;
 //   * optional epilogue: the K dot products x_k . y_k (p.Ap of CG) reduced deterministically across the grid.
@@ -23,11 +24,13 @@ constexpr int SPMM_THREADS = SPMM_NT + 32;
 constexpr int SPMM_MAX_STAGES = 4;
 constexpr int SPMM_RP = SPMM_NT + 8;    // rowptr ints per stage
 constexpr int SPMM_HDR_BYTES = 64 + 1088;   // barriers + reduction scratch
+constexpr int SPMM_BMAX = 64;           // plan: max blocks per CTA (else the on-the-fly producer is used)
 
 struct SpmmArgs {
     int V;
     int stages;             // 2..4
     int cap;                // col/val elements per stage, multiple of 4
+    int hint;               // L2 policy of the matrix stream: 0 none, 1 evict_first, 2 evict_last
     const int *rowptr;
     const int *col;
     const float *val;
@@ -35,8 +38,10 @@ struct SpmmArgs {
     float *y;
     long long ldx, ldy;
     const int *part;        // [gridDim.x + 1] row boundaries, or NULL for an even split
+    const int4 *desc;       // plan: [gridDim.x][SPMM_BMAX] (r0, nr | direct<<16, s_nz, e_nz), or NULL
+    const int *desc_cnt;    // plan: blocks per CTA
     const int *done;        // optional early-exit flag (device), NULL if unused
-    double *partials;       // [gridDim.x * K]   (DOT only)
+    double *partials;       // [K][gridDim.x]    (DOT only)
     unsigned int *ticket;   //                   (DOT only)
     double *dot_out;        // [K]               (DOT only)
 };
@@ -55,7 +60,55 @@ __device__ __forceinline__ void load_x(const float *__restrict__ x, long long ld
     }
 }
 
-template <int K, bool SOA, bool DOT>
+// Decide the extent of the block that starts at row r (nnz offset s_nz): at most NT rows, at most cap-4 elements
+// counted from the 16-byte aligned start.  Returns nr; *e_out = rowptr[r+nr]; *direct = 1 for a row longer than a stage.
+__device__ __forceinline__ int spmm_block_extent(const int *__restrict__ rowptr, int r, int r_end, int s_nz, int cap,
+                                                 int *e_out, int *direct) {
+    int nr = min(SPMM_NT, r_end - r);
+    int e_nz = rowptr[r + nr];
+    const int s_a = s_nz & ~3;
+    *direct = 0;
+    if (e_nz - s_a > cap - 4) {
+        int lo = 0, hi = nr;   // invariant: `lo` rows fit
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (rowptr[r + mid] - s_a <= cap - 4) lo = mid;
+            else hi = mid - 1;
+        }
+        if (lo == 0) {   // a single row longer than a stage: its consumer reads it straight from global
+            nr = 1;
+            *direct = 1;
+        } else {
+            nr = lo;
+        }
+        e_nz = rowptr[r + nr];
+    }
+    *e_out = e_nz;
+    return nr;
+}
+
+// plan kernel: one thread per CTA of the SpMM grid writes that CTA's block descriptors
+static __global__ void spmm_plan_kernel(const int *__restrict__ rowptr, const int *__restrict__ part, int G, int cap,
+                                 int4 *__restrict__ desc, int *__restrict__ desc_cnt, int *__restrict__ overflow) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= G) return;
+    int r = part[c];
+    const int r_end = part[c + 1];
+    int n = 0;
+    int s_nz = (r < r_end) ? rowptr[r] : 0;
+    while (r < r_end) {
+        int e_nz, direct;
+        const int nr = spmm_block_extent(rowptr, r, r_end, s_nz, cap, &e_nz, &direct);
+        if (n < SPMM_BMAX) desc[(size_t)c * SPMM_BMAX + n] = make_int4(r, nr | (direct << 16), s_nz, e_nz);
+        ++n;
+        r += nr;
+        s_nz = e_nz;
+    }
+    desc_cnt[c] = n;
+    if (n > SPMM_BMAX) atomicOr(overflow, 1);
+}
+
+template <int K, bool SOA, bool DOT, int U>
 __global__ void __launch_bounds__(SPMM_THREADS) spmm_tma_kernel(const SpmmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (a.done != nullptr && *reinterpret_cast<const volatile int *>(a.done) != 0) return;
@@ -88,53 +141,69 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm_tma_kernel(const SpmmArgs a
     __syncthreads();
 
     if (tid >= SPMM_NT) {
-        // ===================== producer warp (one elected lane) =====================
-        if (tid == SPMM_NT && r_begin < r_end) {
+        // ===================== producer warp =====================
+        const int lane = tid - SPMM_NT;
+        uint64_t policy = 0;
+        if (a.hint == 1) policy = ls_policy_evict_first();
+        else if (a.hint == 2) policy = ls_policy_evict_last();
+        auto issue = [&](int st, int use, int r, int nr, int direct, int s_nz, int e_nz) {
+            unsigned char *S = stage_base + (size_t)st * stage_bytes;
+            int *hdr = reinterpret_cast<int *>(S);
+            int *s_rp = reinterpret_cast<int *>(S + 16);
+            int *s_col = s_rp + SPMM_RP;
+            float *s_val = reinterpret_cast<float *>(s_col + cap);
+            if (use > 0) ls_mbar_wait(&empty[st], (use - 1) & 1);
+            const int s_a = s_nz & ~3;
+            const int e_a = (e_nz + 3) & ~3;
+            const int r_a = r & ~3;
+            const int rp_n = ((r + nr + 1 + 3) & ~3) - r_a;
+            hdr[0] = r;
+            hdr[1] = nr;
+            hdr[2] = s_a;
+            hdr[3] = direct;
+            const uint32_t nbytes_cv = direct ? 0u : (uint32_t)(e_a - s_a) * 4u;
+            const uint32_t nbytes_rp = (uint32_t)rp_n * 4u;
+            ls_mbar_expect_tx(&full[st], nbytes_rp + 2u * nbytes_cv);
+            ls_bulk_g2s(s_rp, a.rowptr + r_a, nbytes_rp, &full[st]);
+            if (nbytes_cv) {
+                if (a.hint) {
+                    ls_bulk_g2s_hint(s_col, a.col + s_a, nbytes_cv, &full[st], policy);
+                    ls_bulk_g2s_hint(s_val, a.val + s_a, nbytes_cv, &full[st], policy);
+                } else {
+                    ls_bulk_g2s(s_col, a.col + s_a, nbytes_cv, &full[st]);
+                    ls_bulk_g2s(s_val, a.val + s_a, nbytes_cv, &full[st]);
+                }
+            }
+        };
+        if (a.desc != nullptr) {
+            // planned: all descriptors of this CTA arrive with one coalesced load; lane 0 issues
+            const int nb = a.desc_cnt[cta];
+            const int4 *D = a.desc + (size_t)cta * SPMM_BMAX;
+            int4 d0 = (lane < nb) ? D[lane] : make_int4(0, 0, 0, 0);
+            int4 d1 = (lane + 32 < nb) ? D[lane + 32] : make_int4(0, 0, 0, 0);
+            int st = 0, use = 0;
+            for (int b = 0; b < nb; ++b) {
+                const int4 src = (b < 32) ? d0 : d1;
+                int4 d;
+                d.x = __shfl_sync(0xffffffffu, src.x, b & 31);
+                d.y = __shfl_sync(0xffffffffu, src.y, b & 31);
+                d.z = __shfl_sync(0xffffffffu, src.z, b & 31);
+                d.w = __shfl_sync(0xffffffffu, src.w, b & 31);
+                if (lane == 0) issue(st, use, d.x, d.y & 0xffff, d.y >> 16, d.z, d.w);
+                if (++st == stages) {
+                    st = 0;
+                    ++use;
+                }
+            }
+        } else if (lane == 0 && r_begin < r_end) {
+            // unplanned (public SpMM on foreign matrices): block boundaries found on the fly
             int r = r_begin;
             int s_nz = a.rowptr[r];
             int st = 0, use = 0;
             while (r < r_end) {
-                unsigned char *S = stage_base + (size_t)st * stage_bytes;
-                int *hdr = reinterpret_cast<int *>(S);
-                int *s_rp = reinterpret_cast<int *>(S + 16);
-                int *s_col = s_rp + SPMM_RP;
-                float *s_val = reinterpret_cast<float *>(s_col + cap);
-                int nr = min(SPMM_NT, r_end - r);
-                int e_nz = a.rowptr[r + nr];
-                int direct = 0;
-                const int s_a = s_nz & ~3;
-                if (e_nz - s_a > cap - 4) {
-                    // block does not fit the stage: largest nr whose slice fits (binary search on rowptr)
-                    int lo = 0, hi = nr;   // invariant: `lo` rows fit
-                    while (lo < hi) {
-                        int mid = (lo + hi + 1) >> 1;
-                        if (a.rowptr[r + mid] - s_a <= cap - 4) lo = mid;
-                        else hi = mid - 1;
-                    }
-                    if (lo == 0) {   // a single row longer than a stage: its consumer reads it straight from global
-                        nr = 1;
-                        direct = 1;
-                    } else {
-                        nr = lo;
-                    }
-                    e_nz = a.rowptr[r + nr];
-                }
-                if (use > 0) ls_mbar_wait(&empty[st], (use - 1) & 1);
-                const int e_a = (e_nz + 3) & ~3;
-                const int r_a = r & ~3;
-                const int rp_n = ((r + nr + 1 + 3) & ~3) - r_a;
-                hdr[0] = r;
-                hdr[1] = nr;
-                hdr[2] = s_a;
-                hdr[3] = direct;
-                const uint32_t nbytes_cv = direct ? 0u : (uint32_t)(e_a - s_a) * 4u;
-                const uint32_t nbytes_rp = (uint32_t)rp_n * 4u;
-                ls_mbar_expect_tx(&full[st], nbytes_rp + 2u * nbytes_cv);
-                ls_bulk_g2s(s_rp, a.rowptr + r_a, nbytes_rp, &full[st]);
-                if (nbytes_cv) {
-                    ls_bulk_g2s(s_col, a.col + s_a, nbytes_cv, &full[st]);
-                    ls_bulk_g2s(s_val, a.val + s_a, nbytes_cv, &full[st]);
-                }
+                int e_nz, direct;
+                const int nr = spmm_block_extent(a.rowptr, r, r_end, s_nz, cap, &e_nz, &direct);
+                issue(st, use, r, nr, direct, s_nz, e_nz);
                 r += nr;
                 s_nz = e_nz;
                 if (++st == stages) {
@@ -169,37 +238,22 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm_tma_kernel(const SpmmArgs a
                     const int *sc = s_col + (j0 - s_a);
                     const float *sv = s_val + (j0 - s_a);
                     const int len = j1 - j0;
-                    int j = 0;
-                    for (; j + 4 <= len; j += 4) {
-                        int c[4];
-                        float w[4];
-                        float xv[4][K];
+                    // U entries per pass, all gathers of a pass in flight together; slots past the row end are
+                    // predicated to (own row, weight 0) -- an L1 hit that keeps the pass branch-free
+                    for (int j = 0; j < len; j += U) {
+                        int c[U];
+                        float w[U];
+                        float xv[U][K];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            c[u] = sc[j + u];
-                            w[u] = sv[j + u];
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) load_x<K, SOA>(a.x, a.ldx, c[u], xv[u]);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-#pragma unroll
-                            for (int k = 0; k < K; ++k) acc[k] = fmaf(w[u], xv[u][k], acc[k]);
-                    }
-                    if (j < len) {   // 1..3 left: predicated (zero weight, own row as a safe address)
-                        int c[3];
-                        float w[3];
-                        float xv[3][K];
-#pragma unroll
-                        for (int u = 0; u < 3; ++u) {
+                        for (int u = 0; u < U; ++u) {
                             const bool ok = (j + u) < len;
                             c[u] = ok ? sc[j + u] : row;
                             w[u] = ok ? sv[j + u] : 0.f;
                         }
 #pragma unroll
-                        for (int u = 0; u < 3; ++u) load_x<K, SOA>(a.x, a.ldx, c[u], xv[u]);
+                        for (int u = 0; u < U; ++u) load_x<K, SOA>(a.x, a.ldx, c[u], xv[u]);
 #pragma unroll
-                        for (int u = 0; u < 3; ++u)
+                        for (int u = 0; u < U; ++u)
 #pragma unroll
                             for (int k = 0; k < K; ++k) acc[k] = fmaf(w[u], xv[u][k], acc[k]);
                     }
