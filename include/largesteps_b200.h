@@ -68,6 +68,14 @@ int ls_assemble_fill(const void *faces, int idx_bytes, const float *verts, int64
                      int64_t *coo_row, int64_t *coo_col, float *coo_val,
                      int32_t *csr_rowptr, int32_t *csr_col, float *csr_val, void *stream);
 
+/* ---- locality order of the vertices (no reference counterpart: the reference hands the native numbering to
+ *      CHOLMOD, which re-orders internally with AMD; here the solver's matrix copy is re-ordered along a Morton curve
+ *      of the vertex positions so that consecutive rows are a compact patch of the surface) ------------------------
+ *   verts (V,3) float32 device; perm_new2old (V) int32 device out; deterministic.                               */
+int ls_order_workspace_bytes(int64_t V, size_t *bytes_out);
+int ls_order_morton(const float *verts, int64_t V, int32_t *perm_new2old,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- COO -> CSR  (what CholeskySolver.__init__ hands to cholespy: solvers.py:33-34, M.indices(), M.values())
  *   coo_row/coo_col: coalesced, row-major sorted int64 (nnz).  Writes rowptr (V+1) and col (nnz) int32.
  *   Unsorted rows or out-of-range indices -> LS_ERR_INDEX_RANGE (synchronises to report it).            */
@@ -83,7 +91,8 @@ int ls_spmm_csr_f32(int64_t V, const int32_t *rowptr, const int32_t *col, const 
  *      solvers.py:41-126 ConjugateGradientSolver: solve M X = B for all k columns in one pass) ------------
  *   ls_pcg_workspace_bytes: bytes of device workspace a handle for (V, nnz, k_max) needs.
  *   ls_pcg_create: copies the CSR into the (caller-owned, 256-byte aligned) workspace in the solver's padded
- *       streaming layout, extracts the Jacobi diagonal, balances the row partition, builds the CUDA graph.
+ *       streaming layout (re-ordered by perm_new2old when given; b/x/x0 of ls_pcg_solve stay in the caller's
+ *       numbering), extracts the Jacobi diagonal, balances the row partition, plans the SpMM blocks.
  *       The caller keeps `workspace` alive until ls_pcg_destroy.  Synchronises `stream`.
  *       precond: 0 = none, 1 = Jacobi.   k_max in [1,4].
  *   ls_pcg_solve:  b, x: (V,k) float32 row-major contiguous (ld = k); x0 = NULL for a cold start (x0 may alias x).
@@ -95,6 +104,7 @@ int ls_spmm_csr_f32(int64_t V, const int32_t *rowptr, const int32_t *col, const 
 int ls_pcg_workspace_bytes(int64_t V, int64_t nnz, int k_max, size_t *bytes_out);
 int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz,
                   const int32_t *rowptr, const int32_t *col, const float *val,
+                  const int32_t *perm_new2old /* optional locality order from ls_order_morton, or NULL */,
                   int precond, int k_max, void *workspace, size_t workspace_bytes, void *stream);
 int ls_pcg_solve(void *handle, const float *b, float *x, const float *x0, int k,
                  float rtol, int maxit, float *info_dev, float *info_host, void *stream);
@@ -102,6 +112,13 @@ int ls_pcg_destroy(void *handle);
 /* in-solver SpMM of the handle's own matrix copy on SoA planes, for profiling the dominant kernel:
  *   runs `launches` back-to-back launches of the solver's SpMM+dot kernel on its internal p/Ap planes.  */
 int ls_pcg_bench_spmm(void *handle, int k, int launches, void *stream);
+/* timing harness for the iteration kernels, launched back-to-back from C (a Python-level loop is launch-bound):
+ *   `launches` launches rotating over `n_handles` handles (use enough handles that matrix+vectors exceed L2 for an
+ *   HBM-cold number, one handle for the L2-resident number).  which: 0 SpMM+dot, 1 update, 2 p-update, 3 all three. */
+int ls_pcg_bench(void **handles, int n_handles, int k, int which, int launches, void *stream);
+/* introspection: out8 = [engine (1 SELL-32, 0 TMA-staged CSR), padded SELL entries, SpMM grid, vector-kernel grid,
+ *                        CSR stages, CSR stage capacity, block plan valid, re-ordered]                              */
+int ls_pcg_describe(void *handle, int64_t *out8);
 /* algorithmic bytes of one in-solver SpMM launch: 8 nnz + 4 (V+1) + 8 k V  (SURVEY.md section 8 d)      */
 int64_t ls_pcg_spmm_bytes(void *handle, int k);
 

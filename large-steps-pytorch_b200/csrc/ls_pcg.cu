@@ -21,6 +21,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include "ls_spmm_host.h"
+#include "ls_sell_kernel.cuh"
 
 namespace {
 
@@ -61,8 +62,20 @@ struct PcgHandle {
     int vec_grid;
     int4 *desc;
     int *desc_cnt;
+    int *perm;       // new -> old row (NULL-equivalent when has_perm == 0)
+    int *inv;        // old -> new
+    int *scan;
+    int has_perm;
     int planned;
     int vec_mode;
+    // SELL-32 engine (fast path)
+    int *soff;
+    int2 *ent;
+    long long sell_cap;      // capacity of `ent` in entries
+    long long sell_entries;  // padded entry count
+    int nslices;
+    int sell_on;
+    int sell_grid;
     // graphs, one per K
     cudaGraphExec_t graph[KMAX + 1];
     cudaStream_t cap_stream;
@@ -89,11 +102,17 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
     size_t o_dinv = c.take((size_t)Vp * 4);
     size_t o_x = c.take((size_t)Vp * 4 * k_max);
     size_t o_r = c.take((size_t)Vp * 4 * k_max);
-    size_t o_p = c.take((size_t)Vp * 4 * k_max);
+    size_t o_p = c.take((size_t)Vp * 4 * 4);            // p: rows of PW <= 4 floats
     size_t o_Ap = c.take((size_t)Vp * 4 * k_max);
     size_t o_part = c.take((size_t)(grid_cap + 1) * 4);
     size_t o_desc = c.take((size_t)grid_cap * lsk::SPMM_BMAX * sizeof(int4));
     size_t o_dcnt = c.take((size_t)grid_cap * 4);
+    const long long sell_cap = (long long)nnz + nnz / 2 + 32768;
+    size_t o_soff = c.take((size_t)(Vp / 32 + 2) * 4);
+    size_t o_ent = c.take((size_t)sell_cap * 8);
+    size_t o_perm = c.take((size_t)(V + 8) * 4);
+    size_t o_inv = c.take((size_t)(V + 8) * 4);
+    size_t o_scan = c.take(ls_scan_scratch_elems(V + 1) * 4);
     size_t o_ctrl = c.take(sizeof(PcgCtrl));
     size_t o_ps = c.take((size_t)grid_cap * KMAX * 8);
     size_t o_pv = c.take((size_t)grid_cap * 3 * KMAX * 8);
@@ -113,6 +132,13 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
         h->part = (int *)(base + o_part);
         h->desc = (int4 *)(base + o_desc);
         h->desc_cnt = (int *)(base + o_dcnt);
+        h->soff = (int *)(base + o_soff);
+        h->ent = (int2 *)(base + o_ent);
+        h->sell_cap = sell_cap;
+        h->nslices = (int)(Vp / 32);
+        h->perm = (int *)(base + o_perm);
+        h->inv = (int *)(base + o_inv);
+        h->scan = (int *)(base + o_scan);
         h->ctrl = (PcgCtrl *)(base + o_ctrl);
         h->part_spmm = (double *)(base + o_ps);
         h->part_vec = (double *)(base + o_pv);
@@ -159,6 +185,56 @@ __global__ void k_dinv(int64_t V, int64_t Vp, const int *__restrict__ rowptr, co
     dinv[i] = precond ? (1.0f / d) : 1.0f;
 }
 
+// ---- permuted copy  A' = P A P^T  (perm[new] = old) ------------------------------------------------
+__global__ void k_perm_inv_len(int64_t V, const int *__restrict__ perm, const int *__restrict__ rowptr,
+                               int *__restrict__ inv, int *__restrict__ len, int *__restrict__ flags) {
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= V) return;
+    const int o = perm[n];
+    if (o < 0 || o >= V) {
+        atomicOr(flags, 8);
+        len[n] = 0;
+        return;
+    }
+    inv[o] = (int)n;
+    len[n] = rowptr[o + 1] - rowptr[o];
+}
+// one thread per new row: copy the old row with renumbered columns, then insertion-sort it by new column
+__global__ void k_perm_rows(int64_t V, const int *__restrict__ perm, const int *__restrict__ inv,
+                            const int *__restrict__ rowptr, const int *__restrict__ col, const float *__restrict__ val,
+                            const int *__restrict__ rowptr_new, int *__restrict__ col_new, float *__restrict__ val_new,
+                            int *__restrict__ flags) {
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= V) return;
+    const int o = perm[n];
+    if (o < 0 || o >= V) return;
+    const int s = rowptr[o], e = rowptr[o + 1];
+    const int d = rowptr_new[n];
+    for (int j = s; j < e; ++j) {
+        int c = col[j];
+        if (c < 0 || c >= V) {
+            atomicOr(flags, 1);
+            c = o;
+        }
+        const int cn = inv[c];
+        const float w = val[j];
+        int a = d + (j - s) - 1;
+        while (a >= d && col_new[a] > cn) {
+            col_new[a + 1] = col_new[a];
+            val_new[a + 1] = val_new[a];
+            --a;
+        }
+        col_new[a + 1] = cn;
+        val_new[a + 1] = w;
+    }
+}
+__global__ void k_perm_check(int64_t V, const int *__restrict__ perm, const int *__restrict__ inv, int *__restrict__ flags) {
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= V) return;
+    const int o = perm[n];
+    if (o >= 0 && o < V && inv[o] != (int)n) atomicOr(flags, 8);   // not a permutation (duplicate target)
+}
+
 // nnz-balanced contiguous row partition: part[c] = first row r with weight(r) >= c * total / G,
 // weight(r) = 2 * rowptr[r] + 5 * r   (~ bytes/4 streamed per non-zero and per row)
 __global__ void k_partition(int64_t V, const int *__restrict__ rowptr, int G, int *__restrict__ part) {
@@ -188,6 +264,8 @@ struct VecArgs {
     PcgCtrl *ctrl;
     double *partials;
     unsigned int *ticket;
+    const int *perm;   // new -> old row of the caller's (V,K) arrays, or NULL
+    int bench;         // timing harness: ignore the done flag, skip the state transition
 };
 
 // cold start: x = 0, r = b, p = z = dinv r;  warm (stage 2): r = b - Ap (Ap = A x0 from K1), p = z
@@ -201,19 +279,21 @@ __global__ void __launch_bounds__(VEC_THREADS) k_init(VecArgs a, const float *__
     for (int i = 0; i < 3 * K; ++i) acc[i] = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.V; i += (int64_t)gridDim.x * blockDim.x) {
         const float di = a.dinv[i];
+        const int64_t io = a.perm ? a.perm[i] : i;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const float bv = b[i * K + k];
+            const float bv = b[io * K + k];
             float rv = bv;
             if (WARM) rv = bv - a.Ap[(size_t)k * a.Vp + i];
             else a.x[(size_t)k * a.Vp + i] = 0.f;
             const float z = di * rv;
             a.r[(size_t)k * a.Vp + i] = rv;
-            a.p[(size_t)k * a.Vp + i] = z;
+            a.p[(size_t)i * lsk::PRow<K>::PW + k] = z;
             acc[k] += (double)rv * (double)z;
             acc[K + k] += (double)bv * (double)bv;
             acc[2 * K + k] += (double)rv * (double)rv;
         }
+        if (K == 3) a.p[(size_t)i * 4 + 3] = 0.f;
     }
     double tot[3 * K];
     const bool last = ls_grid_reduce<3 * K>(acc, tot, a.partials, a.ticket, red, threadIdx.x, VEC_THREADS, 1,
@@ -255,18 +335,59 @@ __global__ void __launch_bounds__(VEC_THREADS) k_init(VecArgs a, const float *__
 template <int K>
 __global__ void __launch_bounds__(VEC_THREADS) k_warm_load(VecArgs a, const float *__restrict__ x0) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.V; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t io = a.perm ? a.perm[i] : i;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const float v = x0[i * K + k];
+            const float v = x0[io * K + k];
             a.x[(size_t)k * a.Vp + i] = v;
-            a.p[(size_t)k * a.Vp + i] = v;
+            a.p[(size_t)i * lsk::PRow<K>::PW + k] = v;
         }
+        if (K == 3) a.p[(size_t)i * 4 + 3] = 0.f;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) a.ctrl->done = 0;
 }
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+// p is stored as rows of PW floats (PW = 1, 2, 4 for K = 1, 2, 3|4) so that the SpMM gathers one row with one load.
+// These helpers move the 4 rows 4*i4 .. 4*i4+3 between that layout and per-column float4 registers.
+template <int K>
+__device__ __forceinline__ void load_p_rows(const float *p, int64_t i4, float4 (&pv)[K]) {
+    constexpr int PW = lsk::PRow<K>::PW;
+    if (PW == 1) {
+        pv[0] = ld4(p + 4 * i4);
+    } else if (PW == 2) {
+        const float4 a = ld4(p + 8 * i4), b = ld4(p + 8 * i4 + 4);     // rows (0,1) and (2,3)
+        pv[0] = make_float4(a.x, a.z, b.x, b.z);
+        if (K > 1) pv[K > 1 ? 1 : 0] = make_float4(a.y, a.w, b.y, b.w);
+    } else {
+        const float4 r0 = ld4(p + 16 * i4), r1 = ld4(p + 16 * i4 + 4), r2 = ld4(p + 16 * i4 + 8), r3 = ld4(p + 16 * i4 + 12);
+        pv[0] = make_float4(r0.x, r1.x, r2.x, r3.x);
+        if (K > 1) pv[K > 1 ? 1 : 0] = make_float4(r0.y, r1.y, r2.y, r3.y);
+        if (K > 2) pv[K > 2 ? 2 : 0] = make_float4(r0.z, r1.z, r2.z, r3.z);
+        if (K > 3) pv[K > 3 ? 3 : 0] = make_float4(r0.w, r1.w, r2.w, r3.w);
+    }
+}
+template <int K>
+__device__ __forceinline__ void store_p_rows(float *p, int64_t i4, const float4 (&pv)[K]) {
+    constexpr int PW = lsk::PRow<K>::PW;
+    if (PW == 1) {
+        st4(p + 4 * i4, pv[0]);
+    } else if (PW == 2) {
+        const float4 &c0 = pv[0], &c1 = pv[K > 1 ? 1 : 0];
+        st4(p + 8 * i4, make_float4(c0.x, c1.x, c0.y, c1.y));
+        st4(p + 8 * i4 + 4, make_float4(c0.z, c1.z, c0.w, c1.w));
+    } else {
+        const float4 &c0 = pv[0], &c1 = pv[K > 1 ? 1 : 0], &c2 = pv[K > 2 ? 2 : 0];
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 &c3 = (K > 3) ? pv[K > 3 ? 3 : 0] : z;
+        st4(p + 16 * i4, make_float4(c0.x, c1.x, c2.x, c3.x));
+        st4(p + 16 * i4 + 4, make_float4(c0.y, c1.y, c2.y, c3.y));
+        st4(p + 16 * i4 + 8, make_float4(c0.z, c1.z, c2.z, c3.z));
+        st4(p + 16 * i4 + 12, make_float4(c0.w, c1.w, c2.w, c3.w));
+    }
+}
 
 // scalar state transition run by the last CTA of K2: beta, per-column convergence, iteration count, done flag
 template <int K>
@@ -306,17 +427,17 @@ __global__ void __launch_bounds__(VEC_THREADS, 2) k_update(VecArgs a) {
     float4 d, xv[K], pv[K], rv[K], qv[K];
     auto load = [&](int64_t j) {
         d = ld4(a.dinv + 4 * j);
+        load_p_rows<K>(a.p, j, pv);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const size_t o = (size_t)k * a.Vp + 4 * j;
             xv[k] = ld4(a.x + o);
-            pv[k] = ld4(a.p + o);
             rv[k] = ld4(a.r + o);
             qv[k] = ld4(a.Ap + o);
         }
     };
     if (i < n4) load(i);
-    if (*reinterpret_cast<volatile int *>(&c->done) != 0) return;
+    if (!a.bench && *reinterpret_cast<volatile int *>(&c->done) != 0) return;
     float alpha[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -350,7 +471,7 @@ __global__ void __launch_bounds__(VEC_THREADS, 2) k_update(VecArgs a) {
     double tot[2 * K];
     const bool last = ls_grid_reduce<2 * K>(acc, tot, a.partials, a.ticket, red, threadIdx.x, VEC_THREADS, 1,
                                             blockIdx.x, gridDim.x);
-    if (last && threadIdx.x == 0) pcg_transition<K>(c, tot);
+    if (last && threadIdx.x == 0 && !a.bench) pcg_transition<K>(c, tot);
 }
 
 // K3: p = dinv r + beta p   (same loads-first structure as K2)
@@ -363,15 +484,12 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_pupdate(VecArgs a) {
     float4 d, pv[K], rv[K];
     auto load = [&](int64_t j) {
         d = ld4(a.dinv + 4 * j);
+        load_p_rows<K>(a.p, j, pv);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const size_t o = (size_t)k * a.Vp + 4 * j;
-            pv[k] = ld4(a.p + o);
-            rv[k] = ld4(a.r + o);
-        }
+        for (int k = 0; k < K; ++k) rv[k] = ld4(a.r + (size_t)k * a.Vp + 4 * j);
     };
     if (i < n4) load(i);
-    if (*reinterpret_cast<volatile int *>(&c->done) != 0) return;
+    if (!a.bench && *reinterpret_cast<volatile int *>(&c->done) != 0) return;
     float beta[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) beta[k] = c->beta[k];
@@ -379,14 +497,13 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_pupdate(VecArgs a) {
         if (!first) load(i);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const size_t o = (size_t)k * a.Vp + 4 * i;
             const float be = beta[k];
             pv[k].x = fmaf(be, pv[k].x, d.x * rv[k].x);
             pv[k].y = fmaf(be, pv[k].y, d.y * rv[k].y);
             pv[k].z = fmaf(be, pv[k].z, d.z * rv[k].z);
             pv[k].w = fmaf(be, pv[k].w, d.w * rv[k].w);
-            st4(a.p + o, pv[k]);
         }
+        store_p_rows<K>(a.p, i, pv);
     }
 }
 
@@ -394,21 +511,21 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_pupdate(VecArgs a) {
 // ~40 registers -> full occupancy.  Selected with LS_VEC_MODE=1 (sweeps); same arithmetic, same reduction order
 // per column, so results are bitwise identical to the fused-column variants.
 template <int K>
-__global__ void __launch_bounds__(VEC_THREADS, 4) k_update_cs(VecArgs a) {
+__global__ void __launch_bounds__(VEC_THREADS, 3) k_update_cs(VecArgs a) {
     __shared__ double red[2 * K * 32 + 2 * K + 1];
     PcgCtrl *c = a.ctrl;
     const int64_t n4 = a.Vp >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    float4 d = make_float4(0.f, 0.f, 0.f, 0.f), x0, p0, r0, q0;
-    if (i0 < n4) {
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f), x0, r0, q0, pv[K];
+    if (i0 < n4) {   // issued before the dependent scalar chain below
         d = ld4(a.dinv + 4 * i0);
+        load_p_rows<K>(a.p, i0, pv);
         x0 = ld4(a.x + 4 * i0);
-        p0 = ld4(a.p + 4 * i0);
         r0 = ld4(a.r + 4 * i0);
         q0 = ld4(a.Ap + 4 * i0);
     }
-    if (*reinterpret_cast<volatile int *>(&c->done) != 0) return;
+    if (!a.bench && *reinterpret_cast<volatile int *>(&c->done) != 0) return;
     float alpha[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -419,18 +536,22 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_update_cs(VecArgs a) {
 #pragma unroll
     for (int q = 0; q < 2 * K; ++q) acc[q] = 0.0;
     for (int64_t i = i0; i < n4; i += stride) {
-        if (i != i0) d = ld4(a.dinv + 4 * i);
+        if (i != i0) {
+            d = ld4(a.dinv + 4 * i);
+            load_p_rows<K>(a.p, i, pv);
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const size_t o = (size_t)k * a.Vp + 4 * i;
-            float4 xv, pv, rv, qv;
+            float4 xv, rv, qv;
             if (k == 0 && i == i0) {
-                xv = x0; pv = p0; rv = r0; qv = q0;
+                xv = x0; rv = r0; qv = q0;
             } else {
-                xv = ld4(a.x + o); pv = ld4(a.p + o); rv = ld4(a.r + o); qv = ld4(a.Ap + o);
+                xv = ld4(a.x + o); rv = ld4(a.r + o); qv = ld4(a.Ap + o);
             }
             const float al = alpha[k];
-            xv.x = fmaf(al, pv.x, xv.x); xv.y = fmaf(al, pv.y, xv.y); xv.z = fmaf(al, pv.z, xv.z); xv.w = fmaf(al, pv.w, xv.w);
+            const float4 pk = pv[k];
+            xv.x = fmaf(al, pk.x, xv.x); xv.y = fmaf(al, pk.y, xv.y); xv.z = fmaf(al, pk.z, xv.z); xv.w = fmaf(al, pk.w, xv.w);
             rv.x = fmaf(-al, qv.x, rv.x); rv.y = fmaf(-al, qv.y, rv.y); rv.z = fmaf(-al, qv.z, rv.z); rv.w = fmaf(-al, qv.w, rv.w);
             st4(a.x + o, xv);
             st4(a.r + o, rv);
@@ -442,15 +563,16 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_update_cs(VecArgs a) {
     double tot[2 * K];
     const bool last = ls_grid_reduce<2 * K>(acc, tot, a.partials, a.ticket, red, threadIdx.x, VEC_THREADS, 1,
                                             blockIdx.x, gridDim.x);
-    if (last && threadIdx.x == 0) pcg_transition<K>(c, tot);
+    if (last && threadIdx.x == 0 && !a.bench) pcg_transition<K>(c, tot);
 }
 
 // x (SoA) -> out (AoS), info
 template <int K>
 __global__ void __launch_bounds__(VEC_THREADS) k_final(VecArgs a, float *__restrict__ out, float *__restrict__ info) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.V; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t io = a.perm ? a.perm[i] : i;
 #pragma unroll
-        for (int k = 0; k < K; ++k) out[i * K + k] = a.x[(size_t)k * a.Vp + i];
+        for (int k = 0; k < K; ++k) out[io * K + k] = a.x[(size_t)k * a.Vp + i];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const PcgCtrl *c = a.ctrl;
@@ -476,15 +598,18 @@ VecArgs vec_args(PcgHandle *h, int which_ticket) {
     a.ctrl = h->ctrl;
     a.partials = h->part_vec;
     a.ticket = h->tickets + which_ticket;
+    a.perm = h->has_perm ? h->perm : nullptr;
+    a.bench = 0;
     return a;
 }
 
-lsk::SpmmArgs spmm_args(PcgHandle *h, bool with_done) {
+lsk::SpmmArgs spmm_args(PcgHandle *h, int K, bool with_done) {
     lsk::SpmmArgs s{};
     s.V = (int)h->V;
     s.stages = h->cfg.stages;
     s.cap = h->cfg.cap;
     s.hint = h->cfg.hint;
+    s.debug = h->cfg.debug;
     s.desc = h->planned ? h->desc : nullptr;
     s.desc_cnt = h->desc_cnt;
     s.rowptr = h->rowptr;
@@ -492,7 +617,7 @@ lsk::SpmmArgs spmm_args(PcgHandle *h, bool with_done) {
     s.val = h->val;
     s.x = h->p;
     s.y = h->Ap;
-    s.ldx = h->Vp;
+    s.ldx = (K == 1) ? 1 : (K == 2 ? 2 : 4);   // p rows
     s.ldy = h->Vp;
     s.part = h->part;
     s.done = with_done ? &h->ctrl->done : nullptr;
@@ -504,7 +629,24 @@ lsk::SpmmArgs spmm_args(PcgHandle *h, bool with_done) {
 
 template <int K>
 int launch_spmm(PcgHandle *h, bool with_done, cudaStream_t s) {
-    return lsk::spmm_launch(K, true, h->cfg, spmm_args(h, with_done), h->spmm_grid, s);
+    if (h->sell_on) {
+        lsk::SellArgs a{};
+        a.V = (int)h->V;
+        a.nslices = h->nslices;
+        a.soff = h->soff;
+        a.ent = h->ent;
+        a.p = h->p;
+        a.y = h->Ap;
+        a.ldy = h->Vp;
+        a.done = with_done ? &h->ctrl->done : nullptr;
+        a.partials = h->part_spmm;
+        a.ticket = h->tickets + 0;
+        a.dot_out = h->ctrl->pAp;
+        lsk::spmm_sell_kernel<K, true><<<h->sell_grid, lsk::SELL_THREADS, 0, s>>>(a);
+        LS_LAUNCH_CHECK();
+        return LS_OK;
+    }
+    return lsk::spmm_launch(K, true, h->cfg, spmm_args(h, K, with_done), h->spmm_grid, s);
 }
 
 template <int K>
@@ -611,8 +753,8 @@ extern "C" int ls_pcg_workspace_bytes(int64_t V, int64_t nnz, int k_max, size_t 
 }
 
 extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const int32_t *rowptr, const int32_t *col,
-                             const float *val, int precond, int k_max, void *workspace, size_t workspace_bytes,
-                             void *stream_) {
+                             const float *val, const int32_t *perm_new2old, int precond, int k_max, void *workspace,
+                             size_t workspace_bytes, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LS_REQUIRE(handle_out != nullptr, "handle_out is NULL");
     *handle_out = nullptr;
@@ -661,9 +803,28 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
 
     // zero the whole workspace once (padding of every plane must be 0), then copy the CSR in
     TRY_OR_FAIL(cudaMemsetAsync(workspace, 0, need, stream));
-    TRY_OR_FAIL(cudaMemcpyAsync(h->rowptr, rowptr, (size_t)(V + 1) * 4, cudaMemcpyDeviceToDevice, stream));
-    TRY_OR_FAIL(cudaMemcpyAsync(h->col, col, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, stream));
-    TRY_OR_FAIL(cudaMemcpyAsync(h->val, val, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, stream));
+    h->has_perm = perm_new2old ? 1 : 0;
+    if (perm_new2old) {
+        // internal copy in the caller's locality order: A' = P A P^T, rows re-sorted by new column
+        const unsigned gb = (unsigned)((V + 255) / 256);
+        TRY_OR_FAIL(cudaMemcpyAsync(h->perm, perm_new2old, (size_t)V * 4, cudaMemcpyDeviceToDevice, stream));
+        TRY_OR_FAIL(cudaMemsetAsync(h->inv, 0xff, (size_t)V * 4, stream));
+        k_perm_inv_len<<<gb, 256, 0, stream>>>(V, h->perm, rowptr, h->inv, h->rowptr, h->flags);
+        g_ls_launches.fetch_add(1);
+        TRY_OR_FAIL(cudaGetLastError());
+        k_perm_check<<<gb, 256, 0, stream>>>(V, h->perm, h->inv, h->flags);
+        g_ls_launches.fetch_add(1);
+        TRY_OR_FAIL(cudaGetLastError());
+        rc = ls_exclusive_scan_i32(h->rowptr, h->rowptr, V, h->scan, stream);
+        if (rc) return fail(rc);
+        k_perm_rows<<<gb, 256, 0, stream>>>(V, h->perm, h->inv, rowptr, col, val, h->rowptr, h->col, h->val, h->flags);
+        g_ls_launches.fetch_add(1);
+        TRY_OR_FAIL(cudaGetLastError());
+    } else {
+        TRY_OR_FAIL(cudaMemcpyAsync(h->rowptr, rowptr, (size_t)(V + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+        TRY_OR_FAIL(cudaMemcpyAsync(h->col, col, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, stream));
+        TRY_OR_FAIL(cudaMemcpyAsync(h->val, val, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, stream));
+    }
     k_pad_tail<<<1, 32, 0, stream>>>(h->rowptr, h->col, h->val, V, nnz);
     g_ls_launches.fetch_add(1);
     TRY_OR_FAIL(cudaGetLastError());
@@ -690,15 +851,50 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
     g_ls_launches.fetch_add(1);
     TRY_OR_FAIL(cudaGetLastError());
 
+    // SELL-32 copy of the (re-ordered) CSR: the fast in-solver SpMM engine
+    {
+        const unsigned wb = (unsigned)(((int64_t)h->nslices * 32 + 255) / 256);
+        lsk::sell_width_kernel<<<wb, 256, 0, stream>>>((int)V, h->nslices, h->rowptr, h->soff);
+        g_ls_launches.fetch_add(1);
+        TRY_OR_FAIL(cudaGetLastError());
+        rc = ls_exclusive_scan_i32(h->soff, h->soff, h->nslices, h->scan, stream);
+        if (rc) return fail(rc);
+        lsk::sell_fill_kernel<<<wb, 256, 0, stream>>>((int)V, h->nslices, h->rowptr, h->col, h->val, h->soff, h->ent,
+                                                       h->sell_cap);
+        g_ls_launches.fetch_add(1);
+        TRY_OR_FAIL(cudaGetLastError());
+    }
+
     // block plan: every CTA's block boundaries, so the producer warp never chases rowptr at run time
     rc = lsk::spmm_plan(h->rowptr, h->part, h->spmm_grid, h->cfg.cap, h->desc, h->desc_cnt, h->flags + 1, stream);
     if (rc) return fail(rc);
 
     int hflags2[2] = {0, 0};
+    int sell_total = 0;
     TRY_OR_FAIL(cudaMemcpyAsync(hflags2, h->flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    TRY_OR_FAIL(cudaMemcpyAsync(&sell_total, h->soff + h->nslices, sizeof(int), cudaMemcpyDeviceToHost, stream));
     TRY_OR_FAIL(cudaStreamSynchronize(stream));
     const int hflags = hflags2[0];
     h->planned = (hflags2[1] == 0) ? 1 : 0;
+    h->sell_entries = sell_total;
+    {
+        // engine choice: SELL unless padding blew past the buffer (very long rows) or LS_SPMM_ENGINE=csr
+        const char *e = getenv("LS_SPMM_ENGINE");
+        const bool want_csr = e && (e[0] == 'c' || e[0] == 'C');
+        h->sell_on = (!want_csr && sell_total > 0 && (long long)sell_total <= h->sell_cap) ? 1 : 0;
+        int socc = 0;
+        TRY_OR_FAIL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&socc, lsk::spmm_sell_kernel<3, true>, lsk::SELL_THREADS, 0));
+        if (socc < 1) socc = 1;
+        int64_t sg = ((int64_t)h->nslices + lsk::SELL_WARPS - 1) / lsk::SELL_WARPS;   // >= one slice per warp
+        if (sg > (int64_t)di.sm_count * socc) sg = (int64_t)di.sm_count * socc;
+        if (sg > GRID_CAP) sg = GRID_CAP;
+        if (sg < 1) sg = 1;
+        h->sell_grid = (int)sg;
+    }
+    if (hflags & 8) {
+        ls_set_error("perm_new2old is not a permutation of [0, V)");
+        return fail(LS_ERR_BAD_ARG);
+    }
     if (hflags & (1 | 4)) {
         ls_set_error("CSR is malformed (column index out of range or decreasing rowptr)");
         return fail(LS_ERR_INDEX_RANGE);
@@ -753,9 +949,75 @@ extern "C" int ls_pcg_bench_spmm(void *handle, int k, int launches, void *stream
     int rc = lsk::spmm_prepare(k, true, h->cfg, &occ);
     if (rc) return rc;
     for (int i = 0; i < launches; ++i) {
-        rc = lsk::spmm_launch(k, true, h->cfg, spmm_args(h, false), h->spmm_grid, stream);
+        switch (k) {
+            case 1: rc = launch_spmm<1>(h, false, stream); break;
+            case 2: rc = launch_spmm<2>(h, false, stream); break;
+            case 3: rc = launch_spmm<3>(h, false, stream); break;
+            default: rc = launch_spmm<4>(h, false, stream); break;
+        }
         if (rc) return rc;
     }
+    return LS_OK;
+}
+
+namespace {
+template <int K>
+int bench_one(PcgHandle *h, int which, cudaStream_t stream) {
+    int rc = LS_OK;
+    VecArgs va = vec_args(h, 1);
+    va.bench = 1;
+    if (which == 0 || which == 3) rc = launch_spmm<K>(h, false, stream);
+    if (rc) return rc;
+    if (which == 1 || which == 3) {
+        if (h->vec_mode == 1) k_update_cs<K><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va);
+        else k_update<K><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va);
+        LS_LAUNCH_CHECK();
+    }
+    if (which == 2 || which == 3) {
+        k_pupdate<K><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va);
+        LS_LAUNCH_CHECK();
+    }
+    return LS_OK;
+}
+}  // namespace
+
+extern "C" int ls_pcg_bench(void **handles, int n_handles, int k, int which, int launches, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LS_REQUIRE(handles != nullptr && n_handles >= 1, "no handles");
+    LS_REQUIRE(which >= 0 && which <= 3, "which: 0 SpMM, 1 update, 2 p-update, 3 one full iteration");
+    for (int i = 0; i < n_handles; ++i) {
+        PcgHandle *h = (PcgHandle *)handles[i];
+        LS_REQUIRE(h != nullptr, "NULL handle");
+        LS_REQUIRE(k >= 1 && k <= h->k_max, "k out of range for this handle");
+        int occ;
+        int rc = lsk::spmm_prepare(k, true, h->cfg, &occ);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < launches; ++i) {
+        PcgHandle *h = (PcgHandle *)handles[i % n_handles];
+        int rc;
+        switch (k) {
+            case 1: rc = bench_one<1>(h, which, stream); break;
+            case 2: rc = bench_one<2>(h, which, stream); break;
+            case 3: rc = bench_one<3>(h, which, stream); break;
+            default: rc = bench_one<4>(h, which, stream); break;
+        }
+        if (rc) return rc;
+    }
+    return LS_OK;
+}
+
+extern "C" int ls_pcg_describe(void *handle, int64_t *out8) {
+    PcgHandle *h = (PcgHandle *)handle;
+    LS_REQUIRE(h != nullptr && out8 != nullptr, "NULL pointer");
+    out8[0] = h->sell_on;                 // 1 = SELL-32 engine, 0 = TMA-staged CSR engine
+    out8[1] = h->sell_entries;            // padded entries of the SELL copy
+    out8[2] = h->sell_on ? h->sell_grid : h->spmm_grid;
+    out8[3] = h->vec_grid;
+    out8[4] = h->cfg.stages;
+    out8[5] = h->cfg.cap;
+    out8[6] = h->planned;
+    out8[7] = h->has_perm;
     return LS_OK;
 }
 

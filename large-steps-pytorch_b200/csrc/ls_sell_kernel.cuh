@@ -1,0 +1,192 @@
+// ls_sell_kernel.cuh -- in-solver SpMM engine on a SELL-32 copy of the CSR (sm_100a).
+//
+// Why a second engine: ncu + a gather-less diagnostic showed the TMA-staged CSR kernel is *instruction-issue bound*
+// (253 instructions per 7-entry row: per-lane row-length predication, two LDS and three 64-bit address computations +
+// three LDG per non-zero), not memory bound -- 18.5 us with gathers and stores disabled (profiles/r01_*).
+//
+// SELL-32 ("sliced ELLPACK", slice height 32 = one warp): the rows of a slice are padded to the slice's longest row
+// and stored column-major, entry (j, lane) at ent[soff[s] + 32 j + lane] as an int2 {col, val bits}.  Consequences:
+//   * the row loop is warp-uniform (no per-lane predication); padded entries are {own row, 0.0f};
+//   * one coalesced 8-byte load per entry (256 B per warp per slot), streamed with L1::no_allocate;
+//   * the gathered vector p is stored as rows of PW floats (float4 for K=3,4): one LDG.128 and one address per entry
+//     instead of three of each;  ~75 instructions per row instead of 253.
+// The next slice's entries are prefetched into registers while the current slice's gathers are in flight.
+// Bytes streamed per launch: 8 nnz_padded + 4 (V/32+1) + 4 PW V (gather, once) + 4 K V (y) -- within a few % of the
+// CSR algorithmic bytes (padding is ~0.2 % on the plane, <= 15 % on irregular meshes; above 1.5x the CSR engine is used).
+#pragma once
+#include "ls_common.cuh"
+
+namespace lsk {
+
+constexpr int SELL_THREADS = 256;
+constexpr int SELL_WARPS = SELL_THREADS / 32;
+
+struct SellArgs {
+    int V;
+    int nslices;
+    const int *soff;        // [nslices + 1] entry offsets (multiples of 32)
+    const int2 *ent;        // [soff[nslices]] {col, float bits}
+    const float *p;         // gathered vector, rows of PW floats
+    float *y;               // K planes of ldy floats (SoA)
+    long long ldy;
+    const int *done;        // optional early-exit flag
+    double *partials;       // [K][gridDim.x]
+    unsigned int *ticket;
+    double *dot_out;        // [K]
+};
+
+template <int K> struct PRow;
+template <> struct PRow<1> { typedef float T; static constexpr int PW = 1; };
+template <> struct PRow<2> { typedef float2 T; static constexpr int PW = 2; };
+template <> struct PRow<3> { typedef float4 T; static constexpr int PW = 4; };
+template <> struct PRow<4> { typedef float4 T; static constexpr int PW = 4; };
+
+__device__ __forceinline__ void prow_get(const float &v, float (&o)[1]) { o[0] = v; }
+__device__ __forceinline__ void prow_get(const float2 &v, float (&o)[2]) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ void prow_get(const float4 &v, float (&o)[3]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+__device__ __forceinline__ void prow_get(const float4 &v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+
+// streaming 8-byte load of a matrix entry: read-only path, do not allocate in L1 (the gathers own L1)
+__device__ __forceinline__ int2 ld_entry(const int2 *p) {
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+template <int K, bool DOT>
+__global__ void __launch_bounds__(SELL_THREADS) spmm_sell_kernel(const SellArgs a) {
+    typedef typename PRow<K>::T PT;
+    constexpr int U = 8;
+    __shared__ double red[K * 32 + K + 1];
+    if (a.done != nullptr && *reinterpret_cast<const volatile int *>(a.done) != 0) return;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    // contiguous chunk of slices per CTA; its warps interleave over the chunk
+    const int s_begin = (int)((long long)a.nslices * cta / G);
+    const int s_end = (int)((long long)a.nslices * (cta + 1) / G);
+    const PT *__restrict__ prow = reinterpret_cast<const PT *>(a.p);
+
+    double dacc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) dacc[k] = 0.0;
+
+    int s = s_begin + warp;
+    int o0 = 0, o1 = 0;
+    int2 nv[U];
+    if (s < s_end) {
+        o0 = a.soff[s];
+        o1 = a.soff[s + 1];
+        const int w = (o1 - o0) >> 5;
+        const int2 *e = a.ent + o0 + lane;
+#pragma unroll
+        for (int u = 0; u < U; ++u) nv[u] = (u < w) ? ld_entry(e + u * 32) : make_int2(s * 32 + lane, 0);
+    }
+    while (s < s_end) {
+        const int row = s * 32 + lane;
+        const int w = (o1 - o0) >> 5;
+        const int2 *e = a.ent + o0 + lane;
+        int2 cv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) cv[u] = nv[u];
+        // prefetch the first U entries of this warp's next slice
+        const int sn = s + SELL_WARPS;
+        int n0 = 0, n1 = 0;
+        if (sn < s_end) {
+            n0 = a.soff[sn];
+            n1 = a.soff[sn + 1];
+        }
+        float acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.f;
+        // first pass uses the prefetched entries
+        {
+            PT xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = prow[cv[u].x];
+            if (sn < s_end) {
+                const int wn = (n1 - n0) >> 5;
+                const int2 *en = a.ent + n0 + lane;
+#pragma unroll
+                for (int u = 0; u < U; ++u) nv[u] = (u < wn) ? ld_entry(en + u * 32) : make_int2(sn * 32 + lane, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float xk[K];
+                prow_get(xv[u], xk);
+                const float wv = __int_as_float(cv[u].y);
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = fmaf(wv, xk[k], acc[k]);
+            }
+        }
+        // slices wider than U (rare on meshes): remaining passes load their entries directly
+        for (int j = U; j < w; j += U) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) cv[u] = (j + u < w) ? ld_entry(e + (j + u) * 32) : make_int2(row, 0);
+            PT xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = prow[cv[u].x];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float xk[K];
+                prow_get(xv[u], xk);
+                const float wv = __int_as_float(cv[u].y);
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = fmaf(wv, xk[k], acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) a.y[(size_t)k * a.ldy + row] = acc[k];   // planes are padded to 32: no guard
+        if (DOT) {
+            float xr[K];
+            prow_get(prow[row], xr);
+#pragma unroll
+            for (int k = 0; k < K; ++k) dacc[k] += (double)xr[k] * (double)acc[k];
+        }
+        s = sn;
+        o0 = n0;
+        o1 = n1;
+    }
+    if (DOT) {
+        double tot[K];
+        const bool last = ls_grid_reduce<K>(dacc, tot, a.partials, a.ticket, red, tid, SELL_THREADS, 1, cta, G);
+        if (last && tid == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) a.dot_out[k] = tot[k];
+        }
+    }
+}
+
+// ---- SELL build (from the solver's CSR copy) ---------------------------------------------------------
+// widths: one warp per slice, w = max row length; cnt[s] = 32 w
+static __global__ void sell_width_kernel(int V, int nslices, const int *__restrict__ rowptr, int *__restrict__ cnt) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= nslices) return;
+    const int row = gw * 32 + lane;
+    int len = (row < V) ? rowptr[row + 1] - rowptr[row] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if (lane == 0) cnt[gw] = 32 * len;
+}
+static __global__ void sell_fill_kernel(int V, int nslices, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                        const float *__restrict__ val, const int *__restrict__ soff,
+                                        int2 *__restrict__ ent, long long cap_entries) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= nslices) return;
+    const int o0 = soff[gw], o1 = soff[gw + 1];
+    if ((long long)o1 > cap_entries) return;   // over capacity: the caller falls back to the CSR engine
+    const int w = (o1 - o0) >> 5;
+    const int row = gw * 32 + lane;
+    int j0 = 0, len = 0;
+    if (row < V) {
+        j0 = rowptr[row];
+        len = rowptr[row + 1] - j0;
+    }
+    for (int j = 0; j < w; ++j) {
+        int2 v = make_int2(row, 0);                         // padding: own row (inside the padded planes), weight 0
+        if (j < len) v = make_int2(col[j0 + j], __float_as_int(val[j0 + j]));
+        ent[(size_t)o0 + (size_t)j * 32 + lane] = v;
+    }
+}
+
+}  // namespace lsk

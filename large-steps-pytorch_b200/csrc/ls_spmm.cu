@@ -8,7 +8,7 @@ namespace lsk {
 
 // runtime tuning knobs (defaults chosen on B200; LS_SPMM_* environment variables exist for sweeps only)
 void spmm_config(SpmmCfg *cfg) {
-    static SpmmCfg s = {0, 0, 0, 0};
+    static SpmmCfg s = {0, 0, 0, 0, 0};
     if (s.stages == 0) {
         auto geti = [](const char *name, int dflt, int lo, int hi) {
             const char *e = getenv(name);
@@ -17,14 +17,15 @@ void spmm_config(SpmmCfg *cfg) {
         };
         s.stages = geti("LS_SPMM_STAGES", 2, 2, SPMM_MAX_STAGES);
         s.cap = SPMM_NT * geti("LS_SPMM_CAPMUL", 8, 2, 24);
-        s.unroll = geti("LS_SPMM_UNROLL", 8, 4, 8) >= 8 ? 8 : 4;
+        s.unroll = 8;
         s.hint = geti("LS_SPMM_HINT", 1, 0, 2);   // in-solver matrix stream: L2 evict_first
+        s.debug = geti("LS_SPMM_DEBUG", 0, 0, 3);  // diagnostics only
     }
     *cfg = s;
 }
 
 namespace {
-template <int K, bool SOA, bool DOT, int U>
+template <int K, bool X4, bool YSOA, bool DOT, int U>
 int prepare_t(const SpmmCfg &cfg, int *ctas_per_sm) {
     static thread_local int cached_dev = -1, cached_occ = 0, cached_st = 0, cached_cap = 0;
     LsDevInfo di;
@@ -36,9 +37,9 @@ int prepare_t(const SpmmCfg &cfg, int *ctas_per_sm) {
             ls_set_error("SpMM stage configuration needs %zu bytes of shared memory, device allows %d", smem, di.max_smem_optin);
             return LS_ERR_UNSUPPORTED;
         }
-        LS_CUDA_TRY(cudaFuncSetAttribute(spmm_tma_kernel<K, SOA, DOT, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LS_CUDA_TRY(cudaFuncSetAttribute(spmm_tma_kernel<K, X4, YSOA, DOT, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        LS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_tma_kernel<K, SOA, DOT, U>, SPMM_THREADS, smem));
+        LS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_tma_kernel<K, X4, YSOA, DOT, U>, SPMM_THREADS, smem));
         if (occ < 1) occ = 1;
         cached_dev = di.device;
         cached_occ = occ;
@@ -49,10 +50,10 @@ int prepare_t(const SpmmCfg &cfg, int *ctas_per_sm) {
     return LS_OK;
 }
 
-template <int K, bool SOA, bool DOT, int U>
+template <int K, bool X4, bool YSOA, bool DOT, int U>
 int launch_t(const SpmmArgs &a, int grid, cudaStream_t stream) {
     size_t smem = spmm_smem_bytes(a.stages, a.cap);
-    spmm_tma_kernel<K, SOA, DOT, U><<<grid, SPMM_THREADS, smem, stream>>>(a);
+    spmm_tma_kernel<K, X4, YSOA, DOT, U><<<grid, SPMM_THREADS, smem, stream>>>(a);
     LS_LAUNCH_CHECK();
     return LS_OK;
 }
@@ -60,20 +61,19 @@ int launch_t(const SpmmArgs &a, int grid, cudaStream_t stream) {
 
 #define LS_SPMM_DISPATCH(FN, ...)                                                                         \
     do {                                                                                                  \
-        const bool u8 = cfg.unroll >= 8;                                                                  \
-        if (solver_layout) {                                                                              \
+        if (solver_layout) { /* x = solver p rows (1/2/4 floats), y = SoA planes, dot epilogue */          \
             switch (K) {                                                                                  \
-                case 1: return u8 ? FN<1, true, true, 8>(__VA_ARGS__) : FN<1, true, true, 4>(__VA_ARGS__); \
-                case 2: return u8 ? FN<2, true, true, 8>(__VA_ARGS__) : FN<2, true, true, 4>(__VA_ARGS__); \
-                case 3: return u8 ? FN<3, true, true, 8>(__VA_ARGS__) : FN<3, true, true, 4>(__VA_ARGS__); \
-                case 4: return u8 ? FN<4, true, true, 8>(__VA_ARGS__) : FN<4, true, true, 4>(__VA_ARGS__); \
+                case 1: return FN<1, false, true, true, 8>(__VA_ARGS__);                                  \
+                case 2: return FN<2, false, true, true, 8>(__VA_ARGS__);                                  \
+                case 3: return FN<3, true, true, true, 8>(__VA_ARGS__);                                   \
+                case 4: return FN<4, true, true, true, 8>(__VA_ARGS__);                                   \
             }                                                                                             \
-        } else {                                                                                          \
+        } else {             /* public: x, y = (V,k) row-major */                                          \
             switch (K) {                                                                                  \
-                case 1: return u8 ? FN<1, false, false, 8>(__VA_ARGS__) : FN<1, false, false, 4>(__VA_ARGS__); \
-                case 2: return u8 ? FN<2, false, false, 8>(__VA_ARGS__) : FN<2, false, false, 4>(__VA_ARGS__); \
-                case 3: return u8 ? FN<3, false, false, 8>(__VA_ARGS__) : FN<3, false, false, 4>(__VA_ARGS__); \
-                case 4: return u8 ? FN<4, false, false, 8>(__VA_ARGS__) : FN<4, false, false, 4>(__VA_ARGS__); \
+                case 1: return FN<1, false, false, false, 8>(__VA_ARGS__);                                \
+                case 2: return FN<2, false, false, false, 8>(__VA_ARGS__);                                \
+                case 3: return FN<3, false, false, false, 8>(__VA_ARGS__);                                \
+                case 4: return FN<4, false, false, false, 8>(__VA_ARGS__);                                \
             }                                                                                             \
         }                                                                                                 \
         ls_set_error("SpMM: k=%d out of range [1,4]", K);                                                 \

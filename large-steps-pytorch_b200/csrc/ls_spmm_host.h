@@ -4,7 +4,7 @@
 
 namespace lsk {
 struct SpmmCfg {
-    int stages, cap, unroll, hint;
+    int stages, cap, unroll, hint, debug;
 };
 void spmm_config(SpmmCfg *cfg);
 // solver_layout = true: SoA planes + dot epilogue (in-solver); false: AoS, no epilogue (public to_differential)

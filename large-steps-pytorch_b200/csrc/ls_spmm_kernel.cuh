@@ -12,8 +12,10 @@
 //     L1 (neighbouring rows share neighbours, so the gather is mostly L1/L2 hits), and write y coalesced;
 //   * optional epilogue: the K dot products x_k . y_k (p.Ap of CG) reduced deterministically across the grid.
 //
-// Layouts: SOA = K planes of `ld` floats (plane k at base + k*ld; the solver's internal layout);
-//          AOS = (V, K) row-major with leading dimension `ld` (the public torch layout).
+// Layouts: x is always row-major (V, ldx) -- the public torch layout, and the solver's p (rows of 1/2/4 floats; X4 = rows
+//          are 16-byte aligned float4, gathered with one LDG.128); y is row-major (V, ldy) or, YSOA, K planes of ldy floats.
+// In the solver this kernel is the general fallback (very long rows, heavy SELL padding); the fast path is
+// ls_sell_kernel.cuh.
 #pragma once
 #include "ls_common.cuh"
 
@@ -31,6 +33,7 @@ struct SpmmArgs {
     int stages;             // 2..4
     int cap;                // col/val elements per stage, multiple of 4
     int hint;               // L2 policy of the matrix stream: 0 none, 1 evict_first, 2 evict_last
+    int debug;              // diagnostics only (LS_SPMM_DEBUG): 1 = skip the x gathers, 2 = skip the y stores
     const int *rowptr;
     const int *col;
     const float *val;
@@ -49,11 +52,13 @@ struct SpmmArgs {
 inline size_t spmm_stage_bytes(int cap) { return 16 + (size_t)SPMM_RP * 4 + (size_t)cap * 8; }
 inline size_t spmm_smem_bytes(int stages, int cap) { return SPMM_HDR_BYTES + (size_t)stages * spmm_stage_bytes(cap); }
 
-template <int K, bool SOA>
+template <int K, bool X4>
 __device__ __forceinline__ void load_x(const float *__restrict__ x, long long ld, int c, float (&v)[K]) {
-    if (SOA) {
+    if (X4) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(x) + c);
+        const float tt[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-        for (int k = 0; k < K; ++k) v[k] = __ldg(x + (size_t)k * ld + c);
+        for (int k = 0; k < K; ++k) v[k] = tt[k];
     } else {
 #pragma unroll
         for (int k = 0; k < K; ++k) v[k] = __ldg(x + (size_t)c * ld + k);
@@ -108,7 +113,7 @@ static __global__ void spmm_plan_kernel(const int *__restrict__ rowptr, const in
     if (n > SPMM_BMAX) atomicOr(overflow, 1);
 }
 
-template <int K, bool SOA, bool DOT, int U>
+template <int K, bool X4, bool YSOA, bool DOT, int U>
 __global__ void __launch_bounds__(SPMM_THREADS) spmm_tma_kernel(const SpmmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (a.done != nullptr && *reinterpret_cast<const volatile int *>(a.done) != 0) return;
@@ -250,8 +255,15 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm_tma_kernel(const SpmmArgs a
                             c[u] = ok ? sc[j + u] : row;
                             w[u] = ok ? sv[j + u] : 0.f;
                         }
+                        if (a.debug & 1) {
 #pragma unroll
-                        for (int u = 0; u < U; ++u) load_x<K, SOA>(a.x, a.ldx, c[u], xv[u]);
+                            for (int u = 0; u < U; ++u)
+#pragma unroll
+                                for (int k = 0; k < K; ++k) xv[u][k] = (float)(c[u] & 7);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < U; ++u) load_x<K, X4>(a.x, a.ldx, c[u], xv[u]);
+                        }
 #pragma unroll
                         for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -262,12 +274,14 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm_tma_kernel(const SpmmArgs a
                         const int c = __ldg(a.col + j);
                         const float w = __ldg(a.val + j);
                         float xv[K];
-                        load_x<K, SOA>(a.x, a.ldx, c, xv);
+                        load_x<K, X4>(a.x, a.ldx, c, xv);
 #pragma unroll
                         for (int k = 0; k < K; ++k) acc[k] = fmaf(w, xv[k], acc[k]);
                     }
                 }
-                if (SOA) {
+                if (a.debug & 2) {
+                    if (acc[0] == 1.2345e-30f) a.y[row] = acc[0];
+                } else if (YSOA) {
 #pragma unroll
                     for (int k = 0; k < K; ++k) a.y[(size_t)k * a.ldy + row] = acc[k];
                 } else {
@@ -276,7 +290,7 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm_tma_kernel(const SpmmArgs a
                 }
                 if (DOT) {
                     float xr[K];
-                    load_x<K, SOA>(a.x, a.ldx, row, xr);
+                    load_x<K, X4>(a.x, a.ldx, row, xr);
 #pragma unroll
                     for (int k = 0; k < K; ++k) dacc[k] += (double)xr[k] * (double)acc[k];
                 }

@@ -29,13 +29,17 @@ SYMBOLS = {
     "ls_coo_to_csr": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "ls_spmm_csr_f32": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "ls_pcg_workspace_bytes": (c_int, [c_int64, c_int64, c_int, POINTER(c_size_t)]),
-    "ls_pcg_create": (c_int, [POINTER(c_void_p), c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
+    "ls_pcg_create": (c_int, [POINTER(c_void_p), c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                               c_void_p, c_size_t, c_void_p]),
+    "ls_order_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t)]),
+    "ls_order_morton": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ls_pcg_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p,
                              POINTER(c_float), c_void_p]),
     "ls_pcg_destroy": (c_int, [c_void_p]),
     "ls_pcg_bench_spmm": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "ls_pcg_spmm_bytes": (c_int64, [c_void_p, c_int]),
+    "ls_pcg_describe": (c_int, [c_void_p, POINTER(c_int64)]),
+    "ls_pcg_bench": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),
     "ls_adam_uniform_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                      c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
 }

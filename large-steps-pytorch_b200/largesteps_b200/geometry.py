@@ -21,17 +21,42 @@ import torch
 
 from . import _native as N
 
-# id(M) -> (weakref(M), rowptr int32 (V+1), col int32 (nnz), val float32 (nnz))
+ORDER_MIN_V = 8192   # below this everything lives in L1/L2 anyway
+
+# id(M) -> (weakref(M), rowptr int32 (V+1), col int32 (nnz), val float32 (nnz), order int32 (V) or None)
 _csr_cache = {}
 
 
-def _remember_csr(M, rowptr, col, val):
+def _remember_csr(M, rowptr, col, val, order=None):
     key = id(M)
 
     def _drop(_wr, key=key):
         _csr_cache.pop(key, None)
 
-    _csr_cache[key] = (weakref.ref(M, _drop), rowptr, col, val)
+    _csr_cache[key] = (weakref.ref(M, _drop), rowptr, col, val, order)
+
+
+def order_of(M):
+    """Locality order (new -> old vertex, int32) recorded by compute_matrix for this matrix, or None."""
+    ent = _csr_cache.get(id(M))
+    if ent is not None and ent[0]() is M:
+        return ent[4]
+    return None
+
+
+def morton_order(verts):
+    """perm[new] = old along a Morton curve of the vertex positions (csrc/ls_order.cu); deterministic."""
+    N.require_cuda(verts, "verts")
+    v = verts.detach().to(torch.float32).contiguous()
+    V = v.shape[0]
+    perm = torch.empty(V + 8, dtype=torch.int32, device=v.device)[:V]
+    with torch.cuda.device(v.device):
+        nbytes = ctypes.c_size_t(0)
+        N.check(N.lib().ls_order_workspace_bytes(V, ctypes.byref(nbytes)), "ls_order_workspace_bytes")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=v.device)
+        N.check(N.lib().ls_order_morton(N.ptr(v), V, N.ptr(perm), N.ptr(ws), nbytes.value, N.stream_ptr(v.device)),
+                "ls_order_morton")
+    return perm
 
 
 def csr_of(M):
@@ -97,7 +122,9 @@ def _assemble(verts, faces, shift, scale, cotan):
                                      N.ptr(idx[0]), N.ptr(idx[1]), N.ptr(val),
                                      N.ptr(rowptr), N.ptr(col), N.ptr(val), st), "ls_assemble_fill")
     M = torch.sparse_coo_tensor(idx, val, (V, V), is_coalesced=True)
-    _remember_csr(M, rowptr, col, val)
+    # the solver re-orders its private copy of M along a Morton curve of the positions (the public M is untouched)
+    order = morton_order(verts) if V >= ORDER_MIN_V else None
+    _remember_csr(M, rowptr, col, val, order)
     return M
 
 

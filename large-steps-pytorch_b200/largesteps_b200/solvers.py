@@ -17,7 +17,7 @@ import torch
 from torch.autograd import Function
 
 from . import _native as N
-from .geometry import csr_of
+from .geometry import csr_of, order_of
 
 K_MAX = 4   # columns per pass of the native solver (wider right-hand sides are processed in chunks)
 
@@ -45,12 +45,15 @@ class PCGSolver(Solver):
     warm_start : bool   keep the previous solution as the next initial guess, separately for forward and backward
                         solves, as the reference CG does (solvers.py:102-110,120-124)
     strict : bool    raise NotConverged if maxit is reached (otherwise warn and return the last iterate)
+    reorder : bool   let the solver re-order its private matrix copy along the Morton curve recorded by
+                     compute_matrix (pure data-layout change: b and x stay in the caller's vertex numbering)
     """
 
-    def __init__(self, M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, strict=False):
+    def __init__(self, M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, strict=False, reorder=True):
         if precond not in ("jacobi", "none"):
             raise ValueError(f"Unknown preconditioner '{precond}'.")
         rowptr, col, val = csr_of(M)
+        order = order_of(M) if reorder else None
         self.device = val.device
         self.V = int(M.shape[0])
         self.nnz = int(val.shape[0])
@@ -68,7 +71,7 @@ class PCGSolver(Solver):
             N.check(lib.ls_pcg_workspace_bytes(self.V, self.nnz, K_MAX, ctypes.byref(nbytes)), "ls_pcg_workspace_bytes")
             self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)   # owned by this object
             N.check(lib.ls_pcg_create(ctypes.byref(self._handle), self.V, self.nnz, N.ptr(rowptr), N.ptr(col),
-                                      N.ptr(val), 1 if precond == "jacobi" else 0, K_MAX, N.ptr(self._ws),
+                                      N.ptr(val), N.ptr(order), 1 if precond == "jacobi" else 0, K_MAX, N.ptr(self._ws),
                                       nbytes.value, N.stream_ptr(self.device)), "ls_pcg_create")
 
     def __del__(self):
@@ -88,6 +91,12 @@ class PCGSolver(Solver):
     @property
     def relres(self):
         return [float(self._info_host[2 + j]) for j in range(4)]
+
+    def describe(self):
+        out = (ctypes.c_int64 * 8)()
+        N.check(N.lib().ls_pcg_describe(self._handle, out), "ls_pcg_describe")
+        keys = ("sell_engine", "sell_entries", "spmm_grid", "vec_grid", "csr_stages", "csr_cap", "planned", "reordered")
+        return dict(zip(keys, [int(v) for v in out]))
 
     def spmm_bytes(self, k=3):
         return int(N.lib().ls_pcg_spmm_bytes(self._handle, k))
@@ -140,6 +149,15 @@ class PCGSolver(Solver):
             else:
                 self.guess_fwd = x
         return x
+
+
+def bench_kernels(solvers, which, launches, k=3):
+    """Launch `launches` iteration kernels back-to-back from C, rotating over `solvers` (timing harness).
+    which: 0 SpMM+dot, 1 update, 2 p-update, 3 one full iteration."""
+    arr = (ctypes.c_void_p * len(solvers))(*[s._handle for s in solvers])
+    dev = solvers[0].device
+    with torch.cuda.device(dev):
+        N.check(N.lib().ls_pcg_bench(arr, len(solvers), k, which, launches, N.stream_ptr(dev)), "ls_pcg_bench")
 
 
 class CholeskySolver(PCGSolver):

@@ -20,28 +20,40 @@ dev = "cuda:0"
 v, f = workloads.plane(n, seed=0)
 tv, tf = torch.from_numpy(v).to(dev), torch.from_numpy(f).to(dev)
 M = compute_matrix(tv, tf, 1.0, alpha=0.95)
-hs = [PCGSolver(M) for _ in range(4)]
+hs = [PCGSolver(M, reorder=os.environ.get('PROBE_REORDER', '1') == '1') for _ in range(4)]
 u = to_differential(M, tv + 0.01 * torch.randn_like(tv))
 
 
-def timeit(fn, reps):
-    fn()
+from largesteps_b200.solvers import bench_kernels
+
+
+def timeit(which, handles, reps=400):
+    bench_kernels(handles, which, 8)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(reps):
-        fn(i)
+    bench_kernels(handles, which, reps)
     e1.record()
     torch.cuda.synchronize()
     return 1e3 * e0.elapsed_time(e1) / reps
 
 
-L = 400
-cold = timeit(lambda i=0: hs[i % 4].bench_spmm(3, 1), L)
-hot = timeit(lambda i=0: hs[0].bench_spmm(3, 1), L)
-solve = timeit(lambda i=0: hs[0].solve(u), 20)
-it = hs[0].iterations
+out = {"env": {k: v for k, v in os.environ.items() if k.startswith(("LS_", "PROBE_"))}, "n": n, "desc": hs[0].describe()}
+names = ["spmm", "update", "pupdate", "iter3"]
+for w in range(4):
+    out[names[w] + "_cold_us"] = round(timeit(w, hs), 2)
+    out[names[w] + "_hot_us"] = round(timeit(w, hs[:1]), 2)
 B = hs[0].spmm_bytes(3)
-print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("LS_")}, "n": n,
-                  "spmm_cold_us": round(cold, 2), "spmm_hot_us": round(hot, 2), "cold_GBs": round(B / cold / 1e3, 1),
-                  "solve_ms": round(solve / 1e3, 3), "iters": it, "us_per_iter": round(solve / it, 2)}))
+out["spmm_cold_GBs"] = round(B / out["spmm_cold_us"] / 1e3, 1)
+hs[0].solve(u)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(20):
+    hs[0].solve(u)
+e1.record()
+torch.cuda.synchronize()
+out["solve_ms"] = round(e0.elapsed_time(e1) / 20, 3)
+out["iters"] = hs[0].iterations
+out["us_per_iter"] = round(1e3 * out["solve_ms"] / out["iters"], 2)
+print(json.dumps(out))

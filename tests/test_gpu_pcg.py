@@ -146,6 +146,52 @@ def test_warm_start_like_reference_cg():
     assert rel_l2(xt.cpu().numpy(), ds.solve(tiny)) < BAR
 
 
+def test_morton_reorder_is_transparent(bunny_mesh):
+    """The solver's private copy of M is re-ordered along a Morton curve (csrc/ls_order.cu); b and x stay in the
+    caller's numbering, and the answer is the same as without re-ordering."""
+    from largesteps_b200.geometry import morton_order, order_of
+    v, f = bunny_mesh
+    v, f = workloads.subdivide(v, f)
+    v, f = workloads.shuffle_vertices(v.astype(np.float32), f, seed=11)      # worst-case native numbering
+    kw = dict(lambda_=19.0, cotan=True)
+    (r, c, val, V), ds = direct_for(v, f, kw)
+    tv, tf = to_dev(v, f)
+    M = compute_matrix(tv, tf, **kw)
+    perm = order_of(M)
+    assert perm is not None and perm.dtype == torch.int32
+    assert sorted(perm.cpu().tolist()) == list(range(V))                      # a permutation
+    assert torch.equal(perm, morton_order(tv))                                # deterministic
+    # locality: consecutive new rows are close in space (median hop << random-order hop)
+    pv = tv[perm.long()]
+    hop = (pv[1:] - pv[:-1]).norm(dim=1).median().item()
+    hop_native = (tv[1:] - tv[:-1]).norm(dim=1).median().item()
+    assert hop < 0.2 * hop_native
+    _, b, g = rhs(r, c, val, V, v)
+    x_re = PCGSolver(M, reorder=True).solve(t(b))
+    x_no = PCGSolver(M, reorder=False).solve(t(b))
+    xd = ds.solve(b)
+    assert rel_l2(x_re.cpu().numpy(), xd) < BAR and rel_l2(x_no.cpu().numpy(), xd) < BAR
+    assert rel_l2(x_re.cpu().numpy(), x_no.cpu().numpy()) < 2e-6
+    # warm start and backward go through the same permutation
+    s = ConjugateGradientSolver(M)
+    s.solve(t(b))
+    assert rel_l2(s.solve(t(b)).cpu().numpy(), xd) < BAR
+    assert rel_l2(s.solve(t(g), backward=True).cpu().numpy(), ds.solve(g)) < BAR
+    # a bogus permutation is rejected
+    import ctypes
+    from largesteps_b200.geometry import csr_of
+    rowptr, col, vals = csr_of(M)
+    bad = perm.clone()
+    bad[0] = bad[1]
+    nbytes = ctypes.c_size_t(0)
+    N.lib().ls_pcg_workspace_bytes(V, vals.shape[0], 4, ctypes.byref(nbytes))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=DEV)
+    h = ctypes.c_void_p(0)
+    rc = N.lib().ls_pcg_create(ctypes.byref(h), V, vals.shape[0], N.ptr(rowptr), N.ptr(col), N.ptr(vals), N.ptr(bad),
+                               1, 4, N.ptr(ws), nbytes.value, N.stream_ptr(torch.device(DEV)))
+    assert rc == N.LS_ERR_BAD_ARG and "permutation" in N.last_error()
+
+
 def test_deterministic_bitwise():
     v, f = workloads.plane(150, seed=0)
     M = compute_matrix(*to_dev(v, f), 1.0, alpha=0.95)
