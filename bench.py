@@ -284,43 +284,62 @@ def run_b200(args, wl, wl_name):
     e2e_value = world * args.steps / (ms_e2e * 1e-3)
     bytes_io = V * 3 * 4
 
-    # ---- roofline: the dominant kernel (in-solver SpMM + p.Ap) alone, HBM-cold by rotation ----------------
+    # ---- roofline ---------------------------------------------------------------------------------------------
+    # dominant kernel = the persistent solve kernel (one launch per solve): algorithmic bytes per launch = CG
+    # iterations x the per-iteration figure of SURVEY.md 8(d) (SpMM 8 nnz + 4 (V+1) + 8 k V, update 72 MB + 4 MB diag,
+    # p-update 36 MB at V = 1e6: 195.9 MB), divided by the solve's device time from the timed region above.
+    # `spmv` next to it: the stand-alone in-solver SpMM+dot kernel timed alone (CUDA events over 400 launches issued
+    # from C, rotating over 4 copies of matrix + vectors = 336 MB > L2, so every launch streams from HBM).
     roof = None
     if rank == 0:
+        from largesteps_b200.solvers import bench_kernels
+        desc = solver.describe()
+        peak, peak_src = measured_peak()
+        k = 3
+        b_spmm = solver.spmm_bytes(k)
+        b_iter = b_spmm + (6 * k) * 4 * V + 4 * V + (3 * k) * 4 * V
         extra = [PCGSolver(M) for _ in range(3)]
         handles = [solver] + extra
         L = 400
-        for h in handles:
-            h.bench_spmm(3, 2)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(L):
-            handles[i % 4].bench_spmm(3, 1)
-        e1.record()
-        torch.cuda.synchronize()
-        us_per = 1e3 * e0.elapsed_time(e1) / L
-        # same kernel with everything L2-resident (one handle), for contrast
-        e0.record()
-        solver.bench_spmm(3, L)
-        e1.record()
-        torch.cuda.synchronize()
-        us_hot = 1e3 * e0.elapsed_time(e1) / L
-        bytes_alg = solver.spmm_bytes(3)
-        peak, peak_src = measured_peak()
-        ach = bytes_alg / (us_per * 1e-6) / 1e9
+
+        def time_kernels(which, hs):
+            bench_kernels(hs, which, 8)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            bench_kernels(hs, which, L)
+            e1.record()
+            torch.cuda.synchronize()
+            return 1e3 * e0.elapsed_time(e1) / L
+
+        us_cold = time_kernels(0, handles)
+        us_hot = time_kernels(0, handles[:1])
+        spmv = {"kernel": "lsk::spmm_sell_kernel<3,DOT>" if desc["sell_engine"] else "lsk::spmm_tma_kernel<3,...>",
+                "algorithmic_bytes": b_spmm, "us_per_launch": us_cold, "achieved_GBs": b_spmm / (us_cold * 1e-6) / 1e9,
+                "frac": b_spmm / (us_cold * 1e-6) / 1e9 / peak, "l2_resident_us_per_launch": us_hot,
+                "how": "CUDA events over 400 back-to-back launches from C rotating over 4 matrix+vector copies (336 MB > L2)"}
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "solve_traffic.json")
         if os.path.exists(tp) and wl_name == "plane1000":
             try:
                 traffic = json.load(open(tp))["dram_bytes_per_launch"]
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "kernel": "lsk::spmm_tma_kernel<3,SOA,DOT>", "us_per_launch": us_per, "algorithmic_bytes": bytes_alg,
-                "peak_source": peak_src, "l2_resident_us_per_launch": us_hot,
-                "l2_resident_GBs": bytes_alg / (us_hot * 1e-6) / 1e9,
-                "how": "CUDA events over 400 back-to-back launches rotating over 4 matrix+vector copies (336 MB > L2)"}
+        t_solve_s = ms_total * 1e-3 / args.steps
+        if desc["persistent"]:
+            ach = it_mean * b_iter / t_solve_s / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "kernel": "lsp::pcg_persistent_kernel<3,RES=%d> (whole solve, 1 launch)" % (desc["persistent"] - 1),
+                    "algorithmic_bytes": it_mean * b_iter, "algorithmic_bytes_per_iteration": b_iter,
+                    "us_per_launch": 1e6 * t_solve_s, "peak_source": peak_src,
+                    "how": "solve time from the timed region (CUDA events, device-resident RHS); bytes = CG iterations x "
+                           "SURVEY 8(d) per-iteration bytes; r/Ap/dinv stay in shared memory, so DRAM traffic is lower",
+                    "spmv": spmv}
+        else:
+            roof = {"bound": "hbm", "achieved": spmv["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": spmv["frac"],
+                    "traffic": traffic, "kernel": spmv["kernel"], "algorithmic_bytes": b_spmm,
+                    "us_per_launch": us_cold, "peak_source": peak_src, "how": spmv["how"], "spmv": spmv}
+        roof["solver"] = desc
         del extra, handles
 
     clocks = sampler.stop() if rank == 0 else None
@@ -353,7 +372,7 @@ def run_b200(args, wl, wl_name):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl_name, "desc": wl["desc"], "V": V, "nnz": nnz, "rhs_columns": 3,
-                       "solver": "Jacobi-PCG, cold start", "rtol": RTOL, "cg_iterations_mean": it_mean,
+                       "solver": "Jacobi-PCG, cold start, persistent cooperative kernel", "rtol": RTOL, "cg_iterations_mean": it_mean,
                        "parallelism": f"{world} independent mesh(es), one per GPU, no collective on the solve path",
                        "l2": "per-iteration working set ~200 MB > 126 MB L2 and 4 rotating right-hand sides; no explicit flush"},
             "clocks": clocks,

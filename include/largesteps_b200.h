@@ -116,8 +116,12 @@ int ls_pcg_bench_spmm(void *handle, int k, int launches, void *stream);
  *   `launches` launches rotating over `n_handles` handles (use enough handles that matrix+vectors exceed L2 for an
  *   HBM-cold number, one handle for the L2-resident number).  which: 0 SpMM+dot, 1 update, 2 p-update, 3 all three. */
 int ls_pcg_bench(void **handles, int n_handles, int k, int which, int launches, void *stream);
+/* with LS_PCG_PROFILE set in the environment the persistent kernel's CTA 0 accumulates SM-clock cycles per phase of
+ * the last solve: out8 = [SpMM phase, all-reduce 1, update phase, all-reduce 2, p-update phase, barrier 3, 0, iterations] */
+int ls_pcg_phase_cycles(void *handle, int64_t *out, int n /* 8, or 8 + 8*grid for the per-CTA table (.., smid, it) */, void *stream);
 /* introspection: out8 = [engine (1 SELL-32, 0 TMA-staged CSR), padded SELL entries, SpMM grid, vector-kernel grid,
- *                        CSR stages, CSR stage capacity, block plan valid, re-ordered]                              */
+ *                        solve mode (0 graph of 3 kernels / 1 persistent, r+Ap global / 2 persistent, r+Ap in smem),
+ *                        persistent grid, block plan valid, re-ordered]                                             */
 int ls_pcg_describe(void *handle, int64_t *out8);
 /* algorithmic bytes of one in-solver SpMM launch: 8 nnz + 4 (V+1) + 8 k V  (SURVEY.md section 8 d)      */
 int64_t ls_pcg_spmm_bytes(void *handle, int k);

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include "ls_spmm_host.h"
 #include "ls_sell_kernel.cuh"
+#include "ls_pcg_persistent.cuh"
 
 namespace {
 
@@ -76,6 +77,14 @@ struct PcgHandle {
     int nslices;
     int sell_on;
     int sell_grid;
+    // persistent single-kernel solve (K = 3, cold start)
+    lsp::GridBar *gbar;
+    double *part_persist;
+    long long *dbg;
+    unsigned long long *ring;
+    int ring_slots;
+    int persist_on, persist_grid, persist_res, persist_nsl_max;
+    size_t persist_smem;
     // graphs, one per K
     cudaGraphExec_t graph[KMAX + 1];
     cudaStream_t cap_stream;
@@ -116,6 +125,11 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
     size_t o_ctrl = c.take(sizeof(PcgCtrl));
     size_t o_ps = c.take((size_t)grid_cap * KMAX * 8);
     size_t o_pv = c.take((size_t)grid_cap * 3 * KMAX * 8);
+    size_t o_gbar = c.take(64);
+    size_t o_pp = c.take((size_t)2 * lsp::NVMAX * 256 * 8);
+    size_t o_dbg = c.take((size_t)(8 + 8 * 256) * 8);
+    constexpr int RING_SLOTS = 32768;                 // fast all-reduce slots (64 B each): 2 per iteration
+    size_t o_ring = c.take((size_t)RING_SLOTS * 64);
     size_t o_tk = c.take(64);
     size_t o_info = c.take(64);
     size_t o_flags = c.take(64);
@@ -142,6 +156,11 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
         h->ctrl = (PcgCtrl *)(base + o_ctrl);
         h->part_spmm = (double *)(base + o_ps);
         h->part_vec = (double *)(base + o_pv);
+        h->gbar = (lsp::GridBar *)(base + o_gbar);
+        h->part_persist = (double *)(base + o_pp);
+        h->dbg = (long long *)(base + o_dbg);
+        h->ring = (unsigned long long *)(base + o_ring);
+        h->ring_slots = RING_SLOTS;
         h->tickets = (unsigned int *)(base + o_tk);
         h->info = (float *)(base + o_info);
         h->flags = (int *)(base + o_flags);
@@ -681,9 +700,71 @@ int build_graph(PcgHandle *h) {
     return LS_OK;
 }
 
+int finish_info(PcgHandle *h, float rtol, int maxit, float *info_src, float *info_host, cudaStream_t stream) {
+    if (!info_host) return LS_OK;
+    LS_CUDA_TRY(cudaMemcpyAsync(info_host, info_src, 8 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    LS_CUDA_TRY(cudaStreamSynchronize(stream));
+    const int st = (int)info_host[1];
+    if (st == 3) {
+        ls_set_error("CG breakdown after %d iterations (matrix not SPD or NaN in the right-hand side)", (int)info_host[0]);
+        return LS_ERR_BREAKDOWN;
+    }
+    if (st == 2) {
+        ls_set_error("PCG did not reach rtol=%g within maxit=%d (relres %g %g %g %g)", (double)rtol, maxit,
+                     (double)info_host[2], (double)info_host[3], (double)info_host[4], (double)info_host[5]);
+        return LS_ERR_NOT_CONVERGED;
+    }
+    return LS_OK;
+}
+
+int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int maxit, float *info_dev, float *info_host,
+                     cudaStream_t stream) {
+    lsp::PersistArgs a{};
+    a.V = (int)h->V;
+    a.Vp = h->Vp;
+    a.nslices = h->nslices;
+    a.nsl_max = h->persist_nsl_max;
+    a.soff = h->soff;
+    a.ent = h->ent;
+    a.dinv = h->dinv;
+    a.x = h->x;
+    a.r = h->r;
+    a.Ap = h->Ap;
+    a.p = h->p;
+    a.b = b;
+    a.out = x;
+    a.perm = h->has_perm ? h->perm : nullptr;
+    a.rtol = rtol;
+    a.maxit = maxit;
+    a.bar = h->gbar;
+    a.partials = h->part_persist;
+    a.info = info_dev ? info_dev : h->info;
+    a.dbg = getenv("LS_PCG_PROFILE") ? h->dbg : nullptr;
+    LS_CUDA_TRY(cudaMemsetAsync(h->gbar, 0, sizeof(lsp::GridBar), stream));   // barrier counter restarts at 0
+    {
+        // fast all-reduce slots this solve can touch: 2 per iteration (beyond the ring the kernel uses the slow path)
+        long long need = 2LL * maxit + 8;
+        if (need > h->ring_slots) need = h->ring_slots;
+        const char *e = getenv("LS_PCG_FASTRED");
+        a.ring = h->ring;
+        a.ring_slots = (e && e[0] == '0') ? 0 : (h->persist_grid <= 255 ? (int)need : 0);
+        if (a.ring_slots > 0) LS_CUDA_TRY(cudaMemsetAsync(h->ring, 0, (size_t)a.ring_slots * 64, stream));
+    }
+    void *params[] = {(void *)&a};
+    const void *fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, false> : (const void *)lsp::pcg_persistent_kernel<3, 0, false>;
+    if (a.dbg) {   // profiling build of the same kernel (LS_PCG_PROFILE): per-phase cycle counters in CTA 0
+        fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, true> : (const void *)lsp::pcg_persistent_kernel<3, 0, true>;
+        LS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->persist_smem));
+    }
+    LS_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(h->persist_grid), dim3(lsp::PT), params, h->persist_smem, stream));
+    g_ls_launches.fetch_add(1, std::memory_order_relaxed);
+    return finish_info(h, rtol, maxit, a.info, info_host, stream);
+}
+
 template <int K>
 int solve_k(PcgHandle *h, const float *b, float *x, const float *x0, float rtol, int maxit, float *info_dev,
             float *info_host, cudaStream_t stream) {
+    if (K == 3 && h->persist_on && x0 == nullptr) return solve_persistent(h, b, x, rtol, maxit, info_dev, info_host, stream);
     int occ;
     int rc = lsk::spmm_prepare(K, true, h->cfg, &occ);
     if (rc) return rc;
@@ -891,6 +972,43 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
         if (sg < 1) sg = 1;
         h->sell_grid = (int)sg;
     }
+    {
+        // persistent single-kernel solve: one 1024-thread CTA per SM, cooperative launch; r / Ap / dinv in shared memory
+        // when the CTA's rows fit (RES = 1), in global memory otherwise (RES = 0)
+        const char *e = getenv("LS_PCG_MODE");
+        const bool want_graph = e && (e[0] == 'g' || e[0] == 'G');
+        h->persist_on = 0;
+        int coop = 0;
+        TRY_OR_FAIL(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, di.device));
+        if (!want_graph && h->sell_on && coop) {
+            int g = di.sm_count < h->nslices ? di.sm_count : h->nslices;
+            if (g > 256) g = 256;
+            if (g < 1) g = 1;
+            const int nsl_max = (h->nslices + g - 1) / g;
+            const char *er = getenv("LS_PCG_RES");
+            int res = 1;
+            size_t smem = lsp::persist_smem_bytes(3, 1, nsl_max);
+            if ((er && er[0] == '0') || (int)smem > di.max_smem_optin) {
+                res = 0;
+                smem = lsp::persist_smem_bytes(3, 0, nsl_max);
+            }
+            cudaError_t ce = res ? cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                 : cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            int occ = 0;
+            if (ce == cudaSuccess)
+                ce = res ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsp::pcg_persistent_kernel<3, 1, false>, lsp::PT, smem)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsp::pcg_persistent_kernel<3, 0, false>, lsp::PT, smem);
+            if (ce == cudaSuccess && occ >= 1) {
+                h->persist_on = 1;
+                h->persist_grid = g;
+                h->persist_res = res;
+                h->persist_nsl_max = nsl_max;
+                h->persist_smem = smem;
+            } else {
+                cudaGetLastError();   // not fatal: the graph path stays available
+            }
+        }
+    }
     if (hflags & 8) {
         ls_set_error("perm_new2old is not a permutation of [0, V)");
         return fail(LS_ERR_BAD_ARG);
@@ -1007,6 +1125,15 @@ extern "C" int ls_pcg_bench(void **handles, int n_handles, int k, int which, int
     return LS_OK;
 }
 
+extern "C" int ls_pcg_phase_cycles(void *handle, int64_t *out, int n, void *stream_) {
+    PcgHandle *h = (PcgHandle *)handle;
+    LS_REQUIRE(h != nullptr && out != nullptr, "NULL pointer");
+    LS_REQUIRE(n >= 8 && n <= 8 + 8 * 256, "n out of range");
+    LS_CUDA_TRY(cudaMemcpyAsync(out, h->dbg, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+    LS_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream_));
+    return LS_OK;
+}
+
 extern "C" int ls_pcg_describe(void *handle, int64_t *out8) {
     PcgHandle *h = (PcgHandle *)handle;
     LS_REQUIRE(h != nullptr && out8 != nullptr, "NULL pointer");
@@ -1014,8 +1141,8 @@ extern "C" int ls_pcg_describe(void *handle, int64_t *out8) {
     out8[1] = h->sell_entries;            // padded entries of the SELL copy
     out8[2] = h->sell_on ? h->sell_grid : h->spmm_grid;
     out8[3] = h->vec_grid;
-    out8[4] = h->cfg.stages;
-    out8[5] = h->cfg.cap;
+    out8[4] = h->persist_on ? (h->persist_res ? 2 : 1) : 0;   // 0 graph of 3 kernels, 1 persistent (global r/Ap), 2 persistent (smem r/Ap)
+    out8[5] = h->persist_on ? h->persist_grid : 0;
     out8[6] = h->planned;
     out8[7] = h->has_perm;
     return LS_OK;

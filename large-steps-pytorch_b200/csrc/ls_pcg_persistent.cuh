@@ -1,0 +1,569 @@
+// ls_pcg_persistent.cuh -- the whole Jacobi-PCG solve as ONE persistent cooperative kernel (sm_100a).
+//
+// Why: at V = 1e6 every kernel boundary of the 3-kernel iteration costs 3-5 us of launch latency, ramp and drain
+// (a 48 MB p-update takes 10.3 us against 7.4 us of pure streaming), and r / Ap make a round trip through HBM between
+// kernels although only their owner thread ever touches them (profiles/r01_*).
+//
+// Structure: one CTA of 1024 threads per SM, launched cooperatively so that all CTAs are co-resident.  CTA c owns a
+// contiguous range of SELL-32 slices; warp w of the CTA owns slices s_begin + w + 32 i, lane l the row 32 s + l --
+// the SAME thread in every phase.  Per iteration:
+//   phase A   Ap = A p for the owned rows (SELL entries streamed from HBM with register prefetch, p rows gathered
+//             through L1), p.Ap partial                                      -> grid all-reduce #1  (alpha)
+//   phase B   x += alpha p (x in global, owner-only), r -= alpha Ap, r.D^-1 r and r.r partials
+//                                                                           -> grid all-reduce #2  (beta, convergence)
+//   phase C   p = D^-1 r + beta p (p is the only vector other CTAs read)       -> grid barrier   #3  (p visible)
+// r, Ap and D^-1 live in SHARED MEMORY for the whole solve when the CTA's rows fit (RES = 1: 28 B/row, 6784 rows/SM at
+// V = 1e6 = 190 KB of the 227 KB); otherwise (RES = 0) they stay in global memory.  The grid barrier is a
+// generation counter in global memory; the all-reduce writes per-CTA partials before arriving and every CTA re-reduces
+// them in the same fixed order afterwards, so the scalars are bit-identical on every CTA and run to run, and all CTAs
+// take the same convergence decision without another exchange.
+#pragma once
+#include "ls_common.cuh"
+#include "ls_sell_kernel.cuh"
+
+namespace lsp {
+
+constexpr int PT = 768;     // 24 warps: 85 registers per thread (1024 threads forced spills into the SpMM loop)
+constexpr int PWARPS = PT / 32;
+constexpr int NVMAX = 12;
+
+struct GridBar {
+    unsigned int count;
+    unsigned int gen;
+};
+
+struct PersistArgs {
+    int V;
+    long long Vp;
+    int nslices;
+    int nsl_max;            // max slices per CTA (shared-memory sizing)
+    const int *soff;
+    const int2 *ent;
+    const float *dinv;
+    float *x;               // K planes of Vp
+    float *r;               // K planes of Vp   (RES = 0 only)
+    float *Ap;              // K planes of Vp   (RES = 0 only)
+    float *p;               // rows of 4 floats
+    const float *b;         // (V,K) caller layout
+    float *out;             // (V,K) caller layout
+    const int *perm;        // new -> old row, or NULL
+    float rtol;
+    int maxit;
+    GridBar *bar;
+    double *partials;       // [2][NVMAX][gridDim.x]
+    unsigned long long *ring;   // fast all-reduce slots, 8 words each, zeroed by the host before the launch
+    int ring_slots;
+    float *info;            // 8 floats
+    long long *dbg;         // optional [8] cycle counters of CTA 0: A, reduce1, B, reduce2, C, barrier3, init, iterations
+};
+
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_coherent4(const float *p) {   // plain (coherent after a fence), never the .nc path
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid barrier on a monotonically increasing arrival counter (reset to 0 by the host before every launch):
+// barrier number n (1-based) is complete when count >= n * G.  It is split into arrive and wait so that loads which
+// do not depend on other CTAs (the next phase's matrix entries, the owner's own vector rows) are issued in between and
+// their latency overlaps the barrier's (store drain + atomic round trip + poll ~ 2.5 us at 148 CTAs).
+// One thread per CTA arrives / polls; the CTA barrier publishes the result to the rest of the CTA (the pattern
+// cooperative-groups grid.sync uses), so ordinary loads after it see every other CTA's earlier writes.
+__device__ __forceinline__ void grid_arrive(GridBar *gb, unsigned int &gen) {
+    __syncthreads();
+    gen += 1u;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&gb->count, 1u);
+    }
+}
+__device__ __forceinline__ void grid_wait(GridBar *gb, unsigned int gen, int G) {
+    if (threadIdx.x == 0) {
+        const unsigned int target = gen * (unsigned int)G;
+        while ((int)(ld_acquire(&gb->count) - target) < 0) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void grid_barrier(GridBar *gb, unsigned int &gen, int G) {
+    grid_arrive(gb, gen);
+    grid_wait(gb, gen, G);
+}
+
+// deterministic all-reduce of NV doubles per thread across the whole grid, in two halves around one grid barrier
+template <int NV>
+__device__ __forceinline__ void allreduce_arrive(double (&v)[NV], double *partials, GridBar *gb, unsigned int &gen,
+                                                 unsigned int parity, double *red /* >= NV*32 + NV doubles */, int G) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double s = ls_warp_sum(v[i]);
+        if (lane == 0) red[i * 32 + warp] = s;
+    }
+    __syncthreads();
+    double *mine = partials + (size_t)parity * NVMAX * G;
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const double s = ls_warp_sum(lane < PWARPS ? red[i * 32 + lane] : 0.0);
+            if (lane == 0) mine[(size_t)i * G + blockIdx.x] = s;
+        }
+    }
+    grid_arrive(gb, gen);
+}
+template <int NV>
+__device__ __forceinline__ void allreduce_finish(double (&v)[NV], double *partials, GridBar *gb, unsigned int gen,
+                                                 unsigned int &parity, double *red, int G) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    grid_wait(gb, gen, G);
+    const double *mine = partials + (size_t)parity * NVMAX * G;
+    for (int i = warp; i < NV; i += PWARPS) {
+        const double *src = mine + (size_t)i * G;
+        double s = 0.0;
+        for (int c0 = 0; c0 < G; c0 += 256) {
+            double t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j * 32 + lane;
+                t[j] = (c < G) ? __ldcg(src + c) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += t[j];
+        }
+        s = ls_warp_sum(s);
+        if (lane == 0) red[NV * 32 + i] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = red[NV * 32 + i];
+    parity ^= 1u;
+    __syncthreads();   // red[] is reused by the next reduction
+}
+template <int NV>
+__device__ __forceinline__ void grid_allreduce(double (&v)[NV], double *partials, GridBar *gb, unsigned int &gen,
+                                               unsigned int &parity, double *red, int G) {
+    allreduce_arrive<NV>(v, partials, gb, gen, parity, red, G);
+    allreduce_finish<NV>(v, partials, gb, gen, parity, red, G);
+}
+
+struct Scal {                 // CTA-uniform solver scalars, kept in shared memory (identical on every CTA)
+    double rz[4], bb[4], rr[4];
+    float alpha[4], beta[4];
+    int conv[4];
+    int it, status, stop;
+    int e_pAp[4];              // exponent references for the fixed-point all-reduce
+    int e_rzrr[8];             // [rz | rr]
+    int skipA[4], skipB[8];    // frozen columns contribute nothing
+    int nslot;
+};
+
+// ---- fast deterministic all-reduce: one 64-bit atomic per value, no fences, no second pass ------------------------------
+// The slow all-reduce above is a chain of ~6 dependent L2 round trips (partial store -> fence -> arrive -> poll -> fence ->
+// re-read): 8-10k cycles at 148 CTAs, 40 % of an iteration.  Integer addition is associative, so a fixed-point sum is
+// deterministic no matter in which order the CTAs' atomics land.  Word layout:  [63:16] signed fixed-point sum,
+// [15:8] number of CTAs whose partial did not fit ("poison"), [7:0] arrival count.  The scale of value i is taken from
+// the exponent `eref[i]` of the same quantity one iteration earlier (identical on every CTA): a partial must be finite and
+// below 2^(eref+3); 2^-35 relative resolution, far below the fp32 noise of the dot products themselves.  The CTA that adds
+// and the CTAs that poll touch only that word, so nothing needs a fence: r, Ap and x are owner-only, and the only vector
+// other CTAs read (p) is published by the full barrier after phase C.  If any CTA poisons a value, every CTA sees the same
+// poison count and the whole grid repeats that reduction through the slow path.
+template <int NV>
+__device__ __forceinline__ bool fast_allreduce(double (&v)[NV], const int *eref /* smem [NV] */, const int *skip /* smem [NV] */,
+                                               unsigned long long *slot, double *red, int G) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double s = ls_warp_sum(v[i]);
+        if (lane == 0) red[i * 32 + warp] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double mine = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const double s = ls_warp_sum(lane < PWARPS ? red[i * 32 + lane] : 0.0);
+            if (lane == i) mine = s;
+        }
+        if (lane < NV) {
+            const int e = eref[lane];
+            unsigned long long word = 1ull;
+            if (!skip[lane]) {
+                const bool fits = (mine == mine) && (fabs(mine) < ldexp(1.0, e + 3));
+                if (fits) word += ((unsigned long long)llrint(ldexp(mine, 35 - e))) << 16;
+                else word += 1ull << 8;
+            }
+            atomicAdd(slot + lane, word);
+            unsigned long long w;
+            do {
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(slot + lane) : "memory");
+            } while ((int)(w & 0xffull) != G);
+            red[NV * 32 + lane] = ldexp((double)((long long)w >> 16), e - 35);
+            red[NV * 32 + NV + lane] = (double)((w >> 8) & 0xffull);
+        }
+    }
+    __syncthreads();
+    bool poison = false;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        poison |= red[NV * 32 + NV + i] != 0.0;
+    }
+    if (!poison) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = red[NV * 32 + i];
+    }
+    __syncthreads();   // red[] is reused
+    return !poison;
+}
+
+template <int K, int RES, bool PROF>
+__global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs a) {
+    static_assert(K == 3 || K == 4, "persistent kernel is instantiated for float4 p rows");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *red = reinterpret_cast<double *>(smem_raw);                 // NV*32 + NV doubles (NV <= 8)
+    Scal *S = reinterpret_cast<Scal *>(smem_raw + 3072);
+    float *fs = reinterpret_cast<float *>(smem_raw + 4096);
+    const int nsl_max = a.nsl_max;
+    float *r_s = fs;                                                    // [nsl_max][K][32]
+    float *q_s = r_s + (size_t)nsl_max * K * 32;                        // Ap
+    float *d_s = q_s + (size_t)nsl_max * K * 32;                        // dinv [nsl_max][32]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int s_begin = (int)((long long)a.nslices * cta / G);
+    const int s_end = (int)((long long)a.nslices * (cta + 1) / G);
+    const long long Vp = a.Vp;
+    constexpr int U = 8;
+    constexpr int UBB = 2, UBC = 4;    // owned slices processed together in the streaming phases B and C
+
+    unsigned int gen = 0, parity = 0;   // gen = number of grid barriers passed (the host zeroes the counter per launch)
+
+    auto R = [&](int li, int k, int row) -> float & {
+        return RES ? r_s[((size_t)li * K + k) * 32 + lane] : a.r[(size_t)k * Vp + row];
+    };
+    auto Q = [&](int li, int k, int row) -> float & {
+        return RES ? q_s[((size_t)li * K + k) * 32 + lane] : a.Ap[(size_t)k * Vp + row];
+    };
+    long long tA = 0, tR1 = 0, tB = 0, tR2 = 0, tC = 0, tB3 = 0, t0 = 0;
+    const bool prof = PROF && (a.dbg != nullptr) && tid == 0;   // every CTA's thread 0 (per-CTA skew table)
+
+    // ------------------------------------------------------------------ init: x = 0, r = b, p = z = D^-1 r
+    {
+        double acc2[2 * K];
+#pragma unroll
+        for (int i = 0; i < 2 * K; ++i) acc2[i] = 0.0;
+        for (int s = s_begin + warp; s < s_end; s += PWARPS) {
+            const int li = s - s_begin, row = s * 32 + lane;
+            float di = 0.f, bv[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) bv[k] = 0.f;
+            if (row < a.V) {
+                di = a.dinv[row];
+                const long long io = a.perm ? a.perm[row] : row;
+#pragma unroll
+                for (int k = 0; k < K; ++k) bv[k] = a.b[io * K + k];
+            }
+            if (RES) d_s[(size_t)li * 32 + lane] = di;
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                z[k] = di * bv[k];
+                R(li, k, row) = bv[k];
+                a.x[(size_t)k * Vp + row] = 0.f;
+                acc2[k] += (double)bv[k] * (double)z[k];
+                acc2[K + k] += (double)bv[k] * (double)bv[k];
+            }
+            *reinterpret_cast<float4 *>(a.p + 4 * (size_t)row) = make_float4(z[0], z[1], z[2], z[3]);
+        }
+        grid_allreduce<2 * K>(acc2, a.partials, a.bar, gen, parity, red, G);
+        if (tid == 0) {
+            const double rtol2 = (double)a.rtol * (double)a.rtol;
+            int all = 1;
+            for (int k = 0; k < K; ++k) {
+                S->rz[k] = acc2[k];
+                S->bb[k] = acc2[K + k];
+                S->rr[k] = acc2[K + k];
+                S->conv[k] = acc2[K + k] <= rtol2 * acc2[K + k];   // only an all-zero column is converged at entry
+                all &= S->conv[k];
+            }
+            for (int k = 0; k < K; ++k) {
+                const int erz = (acc2[k] > 0.0 && acc2[k] == acc2[k]) ? ilogb(acc2[k]) : -1000;
+                const int ebb = (acc2[K + k] > 0.0 && acc2[K + k] == acc2[K + k]) ? ilogb(acc2[K + k]) : -1000;
+                S->e_pAp[k] = erz + 1;          // p = z at entry and lambda_max(D^-1 M) <= 2 for these matrices
+                S->e_rzrr[k] = erz;
+                S->e_rzrr[K + k] = ebb;
+                S->skipA[k] = S->conv[k];
+                S->skipB[k] = S->skipB[K + k] = S->conv[k];
+            }
+            S->nslot = 0;
+            S->it = 0;
+            S->status = all ? 1 : (a.maxit <= 0 ? 2 : 0);
+            S->stop = S->status != 0;
+        }
+        __syncthreads();
+    }
+
+    // the matrix never changes: the entries of this warp's first slice are (re)loaded BEFORE waiting on the barrier
+    // that ends the previous iteration, so their HBM latency hides under the barrier
+    int o0 = 0, o1 = 0;
+    int2 nv[U];
+    auto prologue = [&]() {
+        const int s = s_begin + warp;
+        if (s < s_end) {
+            o0 = a.soff[s];
+            o1 = a.soff[s + 1];
+            const int w = (o1 - o0) >> 5;
+            const int2 *e = a.ent + o0 + lane;
+#pragma unroll
+            for (int u = 0; u < U; ++u) nv[u] = (u < w) ? lsk::ld_entry(e + u * 32) : make_int2(s * 32 + lane, 0);
+        }
+    };
+    prologue();
+
+    // ------------------------------------------------------------------ iterations
+    while (!S->stop) {
+        // ---------------- phase A: Ap = A p (owned rows), p.Ap
+        if (prof) t0 = clock64();
+        {
+            double dacc[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) dacc[k] = 0.0;
+            int s = s_begin + warp;
+            while (s < s_end) {
+                const int li = s - s_begin, row = s * 32 + lane;
+                const int w = (o1 - o0) >> 5;
+                const int2 *e = a.ent + o0 + lane;
+                int2 cv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) cv[u] = nv[u];
+                const int sn = s + PWARPS;
+                int n0 = 0, n1 = 0;
+                if (sn < s_end) {
+                    n0 = a.soff[sn];
+                    n1 = a.soff[sn + 1];
+                }
+                float acc[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = 0.f;
+                {
+                    float4 xv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) xv[u] = ld_coherent4(a.p + 4 * (size_t)cv[u].x);
+                    if (sn < s_end) {
+                        const int wn = (n1 - n0) >> 5;
+                        const int2 *en = a.ent + n0 + lane;
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            nv[u] = (u < wn) ? lsk::ld_entry(en + u * 32) : make_int2(sn * 32 + lane, 0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float wv = __int_as_float(cv[u].y);
+                        const float xk[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+                        for (int k = 0; k < K; ++k) acc[k] = fmaf(wv, xk[k], acc[k]);
+                    }
+                }
+                for (int j = U; j < w; j += U) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) cv[u] = (j + u < w) ? lsk::ld_entry(e + (j + u) * 32) : make_int2(row, 0);
+                    float4 xv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) xv[u] = ld_coherent4(a.p + 4 * (size_t)cv[u].x);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float wv = __int_as_float(cv[u].y);
+                        const float xk[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+                        for (int k = 0; k < K; ++k) acc[k] = fmaf(wv, xk[k], acc[k]);
+                    }
+                }
+                const float4 po = ld_coherent4(a.p + 4 * (size_t)row);
+                const float pk[4] = {po.x, po.y, po.z, po.w};
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    Q(li, k, row) = acc[k];
+                    dacc[k] += (double)pk[k] * (double)acc[k];
+                }
+                s = sn;
+                o0 = n0;
+                o1 = n1;
+            }
+            if (prof) { const long long t1 = clock64(); tA += t1 - t0; t0 = t1; }
+            {
+                const int ns = S->nslot;
+                bool ok = false;
+                if (ns < a.ring_slots) ok = fast_allreduce<K>(dacc, S->e_pAp, S->skipA, a.ring + 8 * (size_t)ns, red, G);
+                if (!ok) grid_allreduce<K>(dacc, a.partials, a.bar, gen, parity, red, G);
+            }
+            if (tid == 0) {
+                S->nslot += 1;
+                for (int k = 0; k < K; ++k)
+                    if (!S->conv[k] && dacc[k] > 0.0 && dacc[k] == dacc[k]) S->e_pAp[k] = ilogb(dacc[k]);
+                int bad = 0;
+                for (int k = 0; k < K; ++k) {
+                    const bool ok = dacc[k] > 0.0;
+                    if (!S->conv[k] && !ok) bad = 1;
+                    S->alpha[k] = (S->conv[k] || !ok) ? 0.f : (float)(S->rz[k] / dacc[k]);
+                }
+                if (bad) S->status = 3;     // not SPD / NaN: finish this iteration's update with alpha = 0, then stop
+            }
+            __syncthreads();
+            if (prof) { const long long t1 = clock64(); tR1 += t1 - t0; t0 = t1; }
+        }
+        // ---------------- phase B: x += alpha p, r -= alpha Ap, r.z, r.r
+        {
+            float alpha[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) alpha[k] = S->alpha[k];
+            double acc2[2 * K];
+#pragma unroll
+            for (int i = 0; i < 2 * K; ++i) acc2[i] = 0.0;
+            for (int sb = s_begin + warp; sb < s_end; sb += UBB * PWARPS) {
+                float4 po[UBB];
+                float xo[UBB][K];
+#pragma unroll
+                for (int j = 0; j < UBB; ++j) {      // all global loads of UB owned slices in flight together
+                    const int s = sb + j * PWARPS;
+                    if (s < s_end) {
+                        const int row = s * 32 + lane;
+                        po[j] = ld_coherent4(a.p + 4 * (size_t)row);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) xo[j][k] = a.x[(size_t)k * Vp + row];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < UBB; ++j) {
+                    const int s = sb + j * PWARPS;
+                    if (s < s_end) {
+                        const int li = s - s_begin, row = s * 32 + lane;
+                        const float pk[4] = {po[j].x, po[j].y, po[j].z, po[j].w};
+                        const float di = RES ? d_s[(size_t)li * 32 + lane] : a.dinv[row];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            a.x[(size_t)k * Vp + row] = fmaf(alpha[k], pk[k], xo[j][k]);
+                            const float rn = fmaf(-alpha[k], Q(li, k, row), R(li, k, row));
+                            R(li, k, row) = rn;
+                            const float r2 = rn * rn;
+                            acc2[k] += (double)(di * r2);
+                            acc2[K + k] += (double)r2;
+                        }
+                    }
+                }
+            }
+            if (prof) { const long long t1 = clock64(); tB += t1 - t0; t0 = t1; }
+            {
+                const int ns = S->nslot;
+                bool ok = false;
+                if (ns < a.ring_slots) ok = fast_allreduce<2 * K>(acc2, S->e_rzrr, S->skipB, a.ring + 8 * (size_t)ns, red, G);
+                if (!ok) grid_allreduce<2 * K>(acc2, a.partials, a.bar, gen, parity, red, G);
+            }
+            if (tid == 0) {
+                S->nslot += 1;
+                for (int k = 0; k < K; ++k) {
+                    if (S->conv[k]) continue;
+                    if (acc2[k] > 0.0 && acc2[k] == acc2[k]) S->e_rzrr[k] = ilogb(acc2[k]);
+                    if (acc2[K + k] > 0.0 && acc2[K + k] == acc2[K + k]) S->e_rzrr[K + k] = ilogb(acc2[K + k]);
+                }
+                const double rtol2 = (double)a.rtol * (double)a.rtol;
+                int all = 1, bad = (S->status == 3);
+                for (int k = 0; k < K; ++k) {
+                    if (S->conv[k]) {
+                        S->beta[k] = 0.f;
+                        continue;
+                    }
+                    if (!(acc2[k] == acc2[k])) bad = 1;
+                    const double rz_old = S->rz[k];
+                    float be = (rz_old > 0.0) ? (float)(acc2[k] / rz_old) : 0.f;
+                    S->rz[k] = acc2[k];
+                    S->rr[k] = acc2[K + k];
+                    const int cv = acc2[K + k] <= rtol2 * S->bb[k];
+                    S->conv[k] = cv;
+                    if (cv) {
+                        be = 0.f;
+                        S->skipA[k] = 1;
+                        S->skipB[k] = S->skipB[K + k] = 1;
+                    }
+                    S->beta[k] = be;
+                    all &= cv;
+                }
+                const int it = S->it + 1;
+                S->it = it;
+                if (bad) S->status = 3;
+                else if (all) S->status = 1;
+                else if (it >= a.maxit) S->status = 2;
+                S->stop = S->status != 0;
+            }
+            __syncthreads();
+            if (prof) { const long long t1 = clock64(); tR2 += t1 - t0; t0 = t1; }
+        }
+        if (S->stop) break;
+        // ---------------- phase C: p = D^-1 r + beta p, then make p visible
+        {
+            float beta[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) beta[k] = S->beta[k];
+            for (int sb = s_begin + warp; sb < s_end; sb += UBC * PWARPS) {
+                float4 po[UBC];
+#pragma unroll
+                for (int j = 0; j < UBC; ++j) {
+                    const int s = sb + j * PWARPS;
+                    if (s < s_end) po[j] = ld_coherent4(a.p + 4 * (size_t)(s * 32 + lane));
+                }
+#pragma unroll
+                for (int j = 0; j < UBC; ++j) {
+                    const int s = sb + j * PWARPS;
+                    if (s < s_end) {
+                        const int li = s - s_begin, row = s * 32 + lane;
+                        const float di = RES ? d_s[(size_t)li * 32 + lane] : a.dinv[row];
+                        float pn[4] = {po[j].x, po[j].y, po[j].z, po[j].w};
+#pragma unroll
+                        for (int k = 0; k < K; ++k) pn[k] = fmaf(beta[k], pn[k], di * R(li, k, row));
+                        *reinterpret_cast<float4 *>(a.p + 4 * (size_t)row) = make_float4(pn[0], pn[1], pn[2], pn[3]);
+                    }
+                }
+            }
+            if (prof) { const long long t1 = clock64(); tC += t1 - t0; t0 = t1; }
+            grid_arrive(a.bar, gen);
+            prologue();                      // next iteration's first matrix entries fly while the barrier completes
+            grid_wait(a.bar, gen, G);
+            if (prof) { const long long t1 = clock64(); tB3 += t1 - t0; t0 = t1; }
+        }
+    }
+    if (prof) {
+        if (cta == 0) {
+            a.dbg[0] = tA; a.dbg[1] = tR1; a.dbg[2] = tB; a.dbg[3] = tR2; a.dbg[4] = tC; a.dbg[5] = tB3; a.dbg[6] = 0; a.dbg[7] = S->it;
+        }
+        long long *row = a.dbg + 8 + 8 * (size_t)cta;   // per-CTA table
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        row[0] = tA; row[1] = tR1; row[2] = tB; row[3] = tR2; row[4] = tC; row[5] = tB3; row[6] = smid; row[7] = S->it;
+    }
+
+    // ------------------------------------------------------------------ result: x (planes) -> caller layout
+    for (int s = s_begin + warp; s < s_end; s += PWARPS) {
+        const int row = s * 32 + lane;
+        if (row < a.V) {
+            const long long io = a.perm ? a.perm[row] : row;
+#pragma unroll
+            for (int k = 0; k < K; ++k) a.out[io * K + k] = a.x[(size_t)k * Vp + row];
+        }
+    }
+    if (cta == 0 && tid == 0 && a.info) {
+        a.info[0] = (float)S->it;
+        a.info[1] = (float)S->status;
+        for (int k = 0; k < 4; ++k) a.info[2 + k] = (k < K && S->bb[k] > 0.0) ? (float)sqrt(S->rr[k] / S->bb[k]) : 0.f;
+        a.info[6] = a.info[7] = 0.f;
+    }
+}
+
+inline size_t persist_smem_bytes(int K, int res, int nsl_max) {
+    return 4096 + (res ? (size_t)nsl_max * 32 * 4 * (2 * K + 1) : 0);
+}
+
+}  // namespace lsp

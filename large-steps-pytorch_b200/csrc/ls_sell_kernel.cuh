@@ -18,7 +18,7 @@
 
 namespace lsk {
 
-constexpr int SELL_THREADS = 256;
+constexpr int SELL_THREADS = 768;   // one CTA per SM, 24 warps, <= 85 registers (same shape as the persistent solver's phase A)
 constexpr int SELL_WARPS = SELL_THREADS / 32;
 
 struct SellArgs {
@@ -54,7 +54,7 @@ __device__ __forceinline__ int2 ld_entry(const int2 *p) {
 }
 
 template <int K, bool DOT>
-__global__ void __launch_bounds__(SELL_THREADS) spmm_sell_kernel(const SellArgs a) {
+__global__ void __launch_bounds__(SELL_THREADS, 1) spmm_sell_kernel(const SellArgs a) {
     typedef typename PRow<K>::T PT;
     constexpr int U = 8;
     __shared__ double red[K * 32 + K + 1];

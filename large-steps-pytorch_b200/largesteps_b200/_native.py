@@ -40,6 +40,7 @@ SYMBOLS = {
     "ls_pcg_spmm_bytes": (c_int64, [c_void_p, c_int]),
     "ls_pcg_describe": (c_int, [c_void_p, POINTER(c_int64)]),
     "ls_pcg_bench": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p]),
+    "ls_pcg_phase_cycles": (c_int, [c_void_p, POINTER(c_int64), c_int, c_void_p]),
     "ls_adam_uniform_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                      c_float, c_float, c_float, c_float, c_void_p, c_void_p]),
 }

@@ -95,8 +95,20 @@ class PCGSolver(Solver):
     def describe(self):
         out = (ctypes.c_int64 * 8)()
         N.check(N.lib().ls_pcg_describe(self._handle, out), "ls_pcg_describe")
-        keys = ("sell_engine", "sell_entries", "spmm_grid", "vec_grid", "csr_stages", "csr_cap", "planned", "reordered")
+        keys = ("sell_engine", "sell_entries", "spmm_grid", "vec_grid", "persistent", "persistent_grid", "planned", "reordered")
         return dict(zip(keys, [int(v) for v in out]))
+
+    def phase_cycles(self, per_cta=False):
+        g = self.describe()["persistent_grid"] if per_cta else 0
+        n = 8 + 8 * g
+        out = (ctypes.c_int64 * n)()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().ls_pcg_phase_cycles(self._handle, out, n, N.stream_ptr(self.device)), "ls_pcg_phase_cycles")
+        keys = ("spmm", "reduce1", "update", "reduce2", "pupdate", "barrier3", "_", "iterations")
+        d = dict(zip(keys, [int(v) for v in out[:8]]))
+        if per_cta:
+            d["per_cta"] = [[int(out[8 + 8 * c + j]) for j in range(8)] for c in range(g)]
+        return d
 
     def spmm_bytes(self, k=3):
         return int(N.lib().ls_pcg_spmm_bytes(self._handle, k))

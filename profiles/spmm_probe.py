@@ -56,4 +56,15 @@ torch.cuda.synchronize()
 out["solve_ms"] = round(e0.elapsed_time(e1) / 20, 3)
 out["iters"] = hs[0].iterations
 out["us_per_iter"] = round(1e3 * out["solve_ms"] / out["iters"], 2)
+if os.environ.get("LS_PCG_PROFILE"):
+    pc = hs[0].phase_cycles(per_cta=True)
+    itn = max(pc["iterations"], 1)
+    out["phase_cycles_per_iter"] = {k: round(v / itn) for k, v in pc.items() if k not in ("_", "iterations", "per_cta")}
+    import numpy as _np
+    t = _np.array(pc["per_cta"], dtype=_np.float64) / itn
+    for j, nm in enumerate(["spmm", "reduce1", "update", "reduce2", "pupdate", "barrier3"]):
+        out["cta_" + nm] = {"min": round(t[:, j].min()), "med": round(float(_np.median(t[:, j]))), "max": round(t[:, j].max())}
+    order = _np.argsort(t[:, 0])
+    out["slowest_spmm_ctas"] = [(int(c), int(t[c, 6] * itn), round(t[c, 0])) for c in order[-6:]]
+    out["fastest_spmm_ctas"] = [(int(c), int(t[c, 6] * itn), round(t[c, 0])) for c in order[:6]]
 print(json.dumps(out))
