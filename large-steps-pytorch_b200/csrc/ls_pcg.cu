@@ -254,6 +254,28 @@ __global__ void k_perm_check(int64_t V, const int *__restrict__ perm, const int 
     if (o >= 0 && o < V && inv[o] != (int)n) atomicOr(flags, 8);   // not a permutation (duplicate target)
 }
 
+// Gather-locality score of a row order: number of (row, slot) pairs whose column is NOT within 8 entries of the
+// same slot's column in the previous row (adjacent rows are adjacent lanes of a warp, 8 float4 rows of p = one 128-byte
+// line).  Lower is better; used to decide whether the Morton re-ordering actually helps (a row-major grid is already
+// perfectly coalesced, a scanner mesh or a shuffled numbering is not).
+__global__ void k_locality_score(int64_t V, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                 unsigned long long *__restrict__ score) {
+    unsigned int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (int64_t)gridDim.x * blockDim.x) {
+        if ((i & 31) == 0) continue;   // first lane of a warp has no left neighbour
+        const int s = rowptr[i], e = rowptr[i + 1], sp = rowptr[i - 1], ep = rowptr[i];
+        const int n = min(e - s, ep - sp);
+        for (int j = 0; j < n; ++j) {
+            const int d = col[s + j] - col[sp + j];
+            bad += (d < -8 || d > 8) ? 1u : 0u;
+        }
+        bad += (unsigned int)((e - s) - n);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(score, (unsigned long long)bad);
+}
+
 // nnz-balanced contiguous row partition: part[c] = first row r with weight(r) >= c * total / G,
 // weight(r) = 2 * rowptr[r] + 5 * r   (~ bytes/4 streamed per non-zero and per row)
 __global__ void k_partition(int64_t V, const int *__restrict__ rowptr, int G, int *__restrict__ part) {
@@ -885,6 +907,15 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
     // zero the whole workspace once (padding of every plane must be 0), then copy the CSR in
     TRY_OR_FAIL(cudaMemsetAsync(workspace, 0, need, stream));
     h->has_perm = perm_new2old ? 1 : 0;
+    if (perm_new2old && !getenv("LS_FORCE_REORDER")) {
+        // keep the caller's numbering when it already gathers at least as coherently as the Morton order would
+        const unsigned gb = (unsigned)((V + 255) / 256);
+        unsigned long long *sc = reinterpret_cast<unsigned long long *>(h->part_vec);   // scratch, zeroed above
+        k_locality_score<<<gb > 2048 ? 2048 : gb, 256, 0, stream>>>(V, rowptr, col, sc);
+        g_ls_launches.fetch_add(1);
+        TRY_OR_FAIL(cudaGetLastError());
+        // score of the permuted order needs the permuted CSR: build it, score it, then decide
+    }
     if (perm_new2old) {
         // internal copy in the caller's locality order: A' = P A P^T, rows re-sorted by new column
         const unsigned gb = (unsigned)((V + 255) / 256);
@@ -901,6 +932,22 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
         k_perm_rows<<<gb, 256, 0, stream>>>(V, h->perm, h->inv, rowptr, col, val, h->rowptr, h->col, h->val, h->flags);
         g_ls_launches.fetch_add(1);
         TRY_OR_FAIL(cudaGetLastError());
+        if (!getenv("LS_FORCE_REORDER")) {
+            unsigned long long *sc = reinterpret_cast<unsigned long long *>(h->part_vec);
+            k_locality_score<<<gb > 2048 ? 2048 : gb, 256, 0, stream>>>(V, h->rowptr, h->col, sc + 1);
+            g_ls_launches.fetch_add(1);
+            TRY_OR_FAIL(cudaGetLastError());
+            unsigned long long hs[2] = {0, 0};
+            TRY_OR_FAIL(cudaMemcpyAsync(hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, stream));
+            TRY_OR_FAIL(cudaStreamSynchronize(stream));
+            TRY_OR_FAIL(cudaMemsetAsync(sc, 0, sizeof(hs), stream));
+            if (hs[0] <= hs[1]) {   // native order is at least as good: drop the permutation
+                h->has_perm = 0;
+                TRY_OR_FAIL(cudaMemcpyAsync(h->rowptr, rowptr, (size_t)(V + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+                TRY_OR_FAIL(cudaMemcpyAsync(h->col, col, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, stream));
+                TRY_OR_FAIL(cudaMemcpyAsync(h->val, val, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, stream));
+            }
+        }
     } else {
         TRY_OR_FAIL(cudaMemcpyAsync(h->rowptr, rowptr, (size_t)(V + 1) * 4, cudaMemcpyDeviceToDevice, stream));
         TRY_OR_FAIL(cudaMemcpyAsync(h->col, col, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, stream));
@@ -982,7 +1029,8 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
         TRY_OR_FAIL(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, di.device));
         if (!want_graph && h->sell_on && coop) {
             int g = di.sm_count < h->nslices ? di.sm_count : h->nslices;
-            if (g > 256) g = 256;
+            if (h->nslices <= 4 * lsp::PWARPS) g = 1;   // tiny mesh (<= 3K rows): one CTA, grid barriers become __syncthreads
+            if (g > 255) g = 255;
             if (g < 1) g = 1;
             const int nsl_max = (h->nslices + g - 1) / g;
             const char *er = getenv("LS_PCG_RES");

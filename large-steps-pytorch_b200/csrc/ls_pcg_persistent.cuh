@@ -74,15 +74,17 @@ __device__ __forceinline__ float4 ld_coherent4(const float *p) {   // plain (coh
 // their latency overlaps the barrier's (store drain + atomic round trip + poll ~ 2.5 us at 148 CTAs).
 // One thread per CTA arrives / polls; the CTA barrier publishes the result to the rest of the CTA (the pattern
 // cooperative-groups grid.sync uses), so ordinary loads after it see every other CTA's earlier writes.
-__device__ __forceinline__ void grid_arrive(GridBar *gb, unsigned int &gen) {
+__device__ __forceinline__ void grid_arrive(GridBar *gb, unsigned int &gen, int G = 2) {
     __syncthreads();
     gen += 1u;
+    if (G == 1) return;            // single-CTA solve: the CTA barrier is the grid barrier
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(&gb->count, 1u);
     }
 }
 __device__ __forceinline__ void grid_wait(GridBar *gb, unsigned int gen, int G) {
+    if (G == 1) return;
     if (threadIdx.x == 0) {
         const unsigned int target = gen * (unsigned int)G;
         while ((int)(ld_acquire(&gb->count) - target) < 0) {
@@ -92,7 +94,7 @@ __device__ __forceinline__ void grid_wait(GridBar *gb, unsigned int gen, int G) 
     __syncthreads();
 }
 __device__ __forceinline__ void grid_barrier(GridBar *gb, unsigned int &gen, int G) {
-    grid_arrive(gb, gen);
+    grid_arrive(gb, gen, G);
     grid_wait(gb, gen, G);
 }
 
@@ -115,7 +117,7 @@ __device__ __forceinline__ void allreduce_arrive(double (&v)[NV], double *partia
             if (lane == 0) mine[(size_t)i * G + blockIdx.x] = s;
         }
     }
-    grid_arrive(gb, gen);
+    grid_arrive(gb, gen, G);
 }
 template <int NV>
 __device__ __forceinline__ void allreduce_finish(double (&v)[NV], double *partials, GridBar *gb, unsigned int gen,
@@ -190,7 +192,12 @@ __device__ __forceinline__ bool fast_allreduce(double (&v)[NV], const int *eref 
             const double s = ls_warp_sum(lane < PWARPS ? red[i * 32 + lane] : 0.0);
             if (lane == i) mine = s;
         }
-        if (lane < NV) {
+        if (G == 1) {
+            if (lane < NV) {
+                red[NV * 32 + lane] = mine;
+                red[NV * 32 + NV + lane] = 0.0;
+            }
+        } else if (lane < NV) {
             const int e = eref[lane];
             unsigned long long word = 1ull;
             if (!skip[lane]) {
@@ -529,7 +536,7 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
                 }
             }
             if (prof) { const long long t1 = clock64(); tC += t1 - t0; t0 = t1; }
-            grid_arrive(a.bar, gen);
+            grid_arrive(a.bar, gen, G);
             prologue();                      // next iteration's first matrix entries fly while the barrier completes
             grid_wait(a.bar, gen, G);
             if (prof) { const long long t1 = clock64(); tB3 += t1 - t0; t0 = t1; }

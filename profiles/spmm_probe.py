@@ -17,9 +17,20 @@ from largesteps_b200.solvers import PCGSolver
 
 n = int(os.environ.get("PROBE_N", "1000"))
 dev = "cuda:0"
-v, f = workloads.plane(n, seed=0)
+mesh = os.environ.get("PROBE_MESH", "plane")
+if mesh == "ico":
+    v, f = workloads.icosphere(4)
+    kw = dict(lambda_=10.0)
+elif mesh == "bunny":
+    d = np.load(os.path.join(ROOT, "tests", "golden", "bunny_mesh.npz"))
+    v, f = workloads.subdivide(*workloads.subdivide(d["verts"], d["faces"].astype(np.int64)))
+    v = v.astype(np.float32)
+    kw = dict(lambda_=19.0, cotan=True)
+else:
+    v, f = workloads.plane(n, seed=0)
+    kw = dict(lambda_=1.0, alpha=0.95)
 tv, tf = torch.from_numpy(v).to(dev), torch.from_numpy(f).to(dev)
-M = compute_matrix(tv, tf, 1.0, alpha=0.95)
+M = compute_matrix(tv, tf, **kw)
 hs = [PCGSolver(M, reorder=os.environ.get('PROBE_REORDER', '1') == '1') for _ in range(4)]
 u = to_differential(M, tv + 0.01 * torch.randn_like(tv))
 
