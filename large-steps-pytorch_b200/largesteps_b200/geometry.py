@@ -121,7 +121,7 @@ def _assemble(verts, faces, shift, scale, cotan):
                                      float(shift), float(scale), N.ptr(ws), nbytes.value, nnz,
                                      N.ptr(idx[0]), N.ptr(idx[1]), N.ptr(val),
                                      N.ptr(rowptr), N.ptr(col), N.ptr(val), st), "ls_assemble_fill")
-    M = torch.sparse_coo_tensor(idx, val, (V, V), is_coalesced=True)
+    M = torch.sparse_coo_tensor(idx, val, (V, V), is_coalesced=True, check_invariants=False)
     # the solver re-orders its private copy of M along a Morton curve of the positions (the public M is untouched)
     order = morton_order(verts) if V >= ORDER_MIN_V else None
     _remember_csr(M, rowptr, col, val, order)
