@@ -340,9 +340,27 @@ def run_b200(args, wl, wl_name):
                     "traffic": traffic, "kernel": spmv["kernel"], "algorithmic_bytes": b_spmm,
                     "us_per_launch": us_cold, "peak_source": peak_src, "how": spmv["how"], "spmv": spmv}
         roof["solver"] = desc
+        if desc["persistent"]:
+            # in-solver SpMM phase, from the kernel's own per-phase cycle counters (profiling instantiation of the same
+            # kernel, CTA 0): the SpMV as it actually runs inside the solve (Ap stays in shared memory, p comes from L2)
+            os.environ["LS_PCG_PROFILE"] = "1"
+            try:
+                solver.solve(us[0])
+                pc = solver.phase_cycles()
+            finally:
+                del os.environ["LS_PCG_PROFILE"]
+            itn = max(pc["iterations"], 1)
+            roof["phase_cycles_per_iteration"] = {kk: round(vv / itn) for kk, vv in pc.items() if kk not in ("_", "iterations")}
         del extra, handles
 
     clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and roof and "phase_cycles_per_iteration" in roof:
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        cyc = roof["phase_cycles_per_iteration"]["spmm"]
+        us_ph = cyc / mhz
+        roof["spmv_in_solver"] = {"us_per_iteration": us_ph, "sm_mhz": mhz, "algorithmic_bytes": roof["spmv"]["algorithmic_bytes"],
+                                  "achieved_GBs": roof["spmv"]["algorithmic_bytes"] / (us_ph * 1e-6) / 1e9,
+                                  "note": "SpMM phase of the persistent kernel (SM cycles of CTA 0 / SM clock); Ap never leaves shared memory"}
 
     # ---- trivial gather (the only collective): checksum of every rank's last solution ---------------------
     with torch.no_grad():

@@ -740,8 +740,15 @@ int finish_info(PcgHandle *h, float rtol, int maxit, float *info_src, float *inf
 }
 
 int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int maxit, float *info_dev, float *info_host,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, bool resume) {
     lsp::PersistArgs a{};
+    if (resume) {   // warm start: k_warm_load / SpMM / k_init<WARM> left x, r, p and the scalars in global memory
+        a.resume_rz = h->ctrl->rz;
+        a.resume_rr = h->ctrl->rr;
+        a.resume_bb = h->ctrl->bb;
+        a.resume_conv = h->ctrl->conv;
+        a.resume_done = &h->ctrl->done;
+    }
     a.V = (int)h->V;
     a.Vp = h->Vp;
     a.nslices = h->nslices;
@@ -786,7 +793,8 @@ int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int max
 template <int K>
 int solve_k(PcgHandle *h, const float *b, float *x, const float *x0, float rtol, int maxit, float *info_dev,
             float *info_host, cudaStream_t stream) {
-    if (K == 3 && h->persist_on && x0 == nullptr) return solve_persistent(h, b, x, rtol, maxit, info_dev, info_host, stream);
+    if (K == 3 && h->persist_on && x0 == nullptr)
+        return solve_persistent(h, b, x, rtol, maxit, info_dev, info_host, stream, false);
     int occ;
     int rc = lsk::spmm_prepare(K, true, h->cfg, &occ);
     if (rc) return rc;
@@ -802,6 +810,8 @@ int solve_k(PcgHandle *h, const float *b, float *x, const float *x0, float rtol,
         LS_LAUNCH_CHECK();
         k_init<K, false><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, b, rtol, maxit, 1);   // runs only if `restart`
         LS_LAUNCH_CHECK();
+        if (K == 3 && h->persist_on)   // iterate in the persistent kernel from the state the three kernels above left
+            return solve_persistent(h, b, x, rtol, maxit, info_dev, info_host, stream, true);
     } else {
         k_init<K, false><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, b, rtol, maxit, 0);
         LS_LAUNCH_CHECK();

@@ -51,6 +51,9 @@ struct PersistArgs {
     int maxit;
     GridBar *bar;
     double *partials;       // [2][NVMAX][gridDim.x]
+    // resume mode (warm start): x, r (planes) and p (rows) were initialised by the graph-mode kernels; scalars come from here
+    const double *resume_rz, *resume_rr, *resume_bb;   // [4] each, or NULL for a cold start
+    const int *resume_conv, *resume_done;
     unsigned long long *ring;   // fast all-reduce slots, 8 words each, zeroed by the host before the launch
     int ring_slots;
     float *info;            // 8 floats
@@ -259,6 +262,40 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
     long long tA = 0, tR1 = 0, tB = 0, tR2 = 0, tC = 0, tB3 = 0, t0 = 0;
     const bool prof = PROF && (a.dbg != nullptr) && tid == 0;   // every CTA's thread 0 (per-CTA skew table)
 
+    // ------------------------------------------------------------------ resume (warm start): state is in global memory
+    if (a.resume_rz != nullptr) {
+        for (int s = s_begin + warp; s < s_end; s += PWARPS) {
+            const int li = s - s_begin, row = s * 32 + lane;
+            if (RES) {
+                d_s[(size_t)li * 32 + lane] = a.dinv[row];
+#pragma unroll
+                for (int k = 0; k < K; ++k) r_s[((size_t)li * K + k) * 32 + lane] = a.r[(size_t)k * Vp + row];
+            }
+        }
+        if (tid == 0) {
+            int all = 1;
+            for (int k = 0; k < K; ++k) {
+                const double rz = a.resume_rz[k], rr = a.resume_rr[k], bb = a.resume_bb[k];
+                S->rz[k] = rz;
+                S->rr[k] = rr;
+                S->bb[k] = bb;
+                S->conv[k] = a.resume_conv[k];
+                all &= S->conv[k];
+                const int erz = (rz > 0.0 && rz == rz) ? ilogb(rz) : -1000;
+                const int err = (rr > 0.0 && rr == rr) ? ilogb(rr) : -1000;
+                S->e_pAp[k] = erz + 1;
+                S->e_rzrr[k] = erz;
+                S->e_rzrr[K + k] = err;
+                S->skipA[k] = S->conv[k];
+                S->skipB[k] = S->skipB[K + k] = S->conv[k];
+            }
+            S->nslot = 0;
+            S->it = 0;
+            S->status = (all || *a.resume_done == 1) ? 1 : (a.maxit <= 0 ? 2 : 0);
+            S->stop = S->status != 0;
+        }
+        __syncthreads();
+    } else
     // ------------------------------------------------------------------ init: x = 0, r = b, p = z = D^-1 r
     {
         double acc2[2 * K];

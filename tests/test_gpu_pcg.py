@@ -192,6 +192,39 @@ def test_morton_reorder_is_transparent(bunny_mesh):
     assert rc == N.LS_ERR_BAD_ARG and "permutation" in N.last_error()
 
 
+@pytest.mark.parametrize("env", [
+    {},                                   # default: persistent kernel, r/Ap in shared memory, fixed-point all-reduce
+    {"LS_PCG_RES": "0"},                  # persistent kernel, r/Ap in global memory
+    {"LS_PCG_FASTRED": "0"},              # persistent kernel, fenced partial-array all-reduce
+    {"LS_PCG_MODE": "graph"},             # CUDA graph of 3 kernels per iteration, SELL SpMM engine
+    {"LS_PCG_MODE": "graph", "LS_SPMM_ENGINE": "csr"},   # ... with the TMA-staged CSR SpMM engine
+    {"LS_FORCE_REORDER": "1"},            # Morton re-ordered private copy
+])
+def test_every_solver_mode_meets_the_bar(env, bunny_mesh, monkeypatch):
+    """All execution modes of the solve (selected at handle creation) give the direct-solve answer."""
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    cases = [config2(bunny_mesh), (*workloads.plane(260, seed=1), dict(lambda_=1.0, alpha=0.95))]
+    for v, f, kw in cases:
+        (r, c, val, V), ds = direct_for(v, f, kw)
+        _, b, g = rhs(r, c, val, V, v)
+        M = compute_matrix(*to_dev(v, f), **kw)
+        s = PCGSolver(M)
+        d = s.describe()
+        if env.get("LS_PCG_MODE") == "graph":
+            assert d["persistent"] == 0
+        elif env.get("LS_PCG_RES") == "0":
+            assert d["persistent"] == 1
+        else:
+            assert d["persistent"] == 2
+        assert d["sell_engine"] == (0 if env.get("LS_SPMM_ENGINE") == "csr" else 1)
+        if "LS_FORCE_REORDER" in env:
+            assert d["reordered"] == 1
+        assert rel_l2(s.solve(t(b)).cpu().numpy(), ds.solve(b)) < BAR
+        assert rel_l2(s.solve(t(g), backward=True).cpu().numpy(), ds.solve(g)) < BAR
+        assert 0 < s.iterations < 1000 and max(s.relres[:3]) <= 1.01e-7
+
+
 def test_deterministic_bitwise():
     v, f = workloads.plane(150, seed=0)
     M = compute_matrix(*to_dev(v, f), 1.0, alpha=0.95)
