@@ -249,7 +249,11 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
     const int s_end = (int)((long long)a.nslices * (cta + 1) / G);
     const long long Vp = a.Vp;
     constexpr int U = 8;
-    constexpr int UBB = 2, UBC = 4;    // owned slices processed together in the streaming phases B and C
+    constexpr int UBC = 3;    // owned slices whose global loads are in flight together in phase C
+#ifndef LS_PREFC
+#define LS_PREFC 1
+#endif
+    constexpr bool PREFC = (LS_PREFC != 0);   // prefetch phase C's first batch across all-reduce 2
 
     unsigned int gen = 0, parity = 0;   // gen = number of grid barriers passed (the host zeroes the counter per launch)
 
@@ -394,6 +398,7 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
                 float acc[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) acc[k] = 0.f;
+                float4 po = make_float4(0.f, 0.f, 0.f, 0.f);   // own row of p: it is one of the gathered rows (diagonal entry)
                 {
                     float4 xv[U];
 #pragma unroll
@@ -409,6 +414,7 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
                     for (int u = 0; u < U; ++u) {
                         const float wv = __int_as_float(cv[u].y);
                         const float xk[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                        if (cv[u].x == row) po = xv[u];
 #pragma unroll
                         for (int k = 0; k < K; ++k) acc[k] = fmaf(wv, xk[k], acc[k]);
                     }
@@ -423,11 +429,11 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
                     for (int u = 0; u < U; ++u) {
                         const float wv = __int_as_float(cv[u].y);
                         const float xk[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                        if (cv[u].x == row) po = xv[u];
 #pragma unroll
                         for (int k = 0; k < K; ++k) acc[k] = fmaf(wv, xk[k], acc[k]);
                     }
                 }
-                const float4 po = ld_coherent4(a.p + 4 * (size_t)row);
                 const float pk[4] = {po.x, po.y, po.z, po.w};
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
@@ -460,7 +466,9 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
             __syncthreads();
             if (prof) { const long long t1 = clock64(); tR1 += t1 - t0; t0 = t1; }
         }
-        // ---------------- phase B: x += alpha p, r -= alpha Ap, r.z, r.r
+        // ---------------- phase B: r -= alpha Ap, r.z, r.r   (x += alpha p is folded into phase C)
+        float4 pc0[UBC];
+        float xc0[UBC][K];
         {
             float alpha[K];
 #pragma unroll
@@ -468,39 +476,33 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
             double acc2[2 * K];
 #pragma unroll
             for (int i = 0; i < 2 * K; ++i) acc2[i] = 0.0;
-            for (int sb = s_begin + warp; sb < s_end; sb += UBB * PWARPS) {
-                float4 po[UBB];
-                float xo[UBB][K];
+            // r, Ap and D^-1 are in shared memory (RES = 1): this phase touches no global memory at all; the x update
+            // that belongs here is done in phase C, which reads the owner's p row anyway
+            for (int s = s_begin + warp; s < s_end; s += PWARPS) {
+                const int li = s - s_begin, row = s * 32 + lane;
+                const float di = RES ? d_s[(size_t)li * 32 + lane] : a.dinv[row];
 #pragma unroll
-                for (int j = 0; j < UBB; ++j) {      // all global loads of UB owned slices in flight together
-                    const int s = sb + j * PWARPS;
-                    if (s < s_end) {
-                        const int row = s * 32 + lane;
-                        po[j] = ld_coherent4(a.p + 4 * (size_t)row);
-#pragma unroll
-                        for (int k = 0; k < K; ++k) xo[j][k] = a.x[(size_t)k * Vp + row];
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < UBB; ++j) {
-                    const int s = sb + j * PWARPS;
-                    if (s < s_end) {
-                        const int li = s - s_begin, row = s * 32 + lane;
-                        const float pk[4] = {po[j].x, po[j].y, po[j].z, po[j].w};
-                        const float di = RES ? d_s[(size_t)li * 32 + lane] : a.dinv[row];
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            a.x[(size_t)k * Vp + row] = fmaf(alpha[k], pk[k], xo[j][k]);
-                            const float rn = fmaf(-alpha[k], Q(li, k, row), R(li, k, row));
-                            R(li, k, row) = rn;
-                            const float r2 = rn * rn;
-                            acc2[k] += (double)(di * r2);
-                            acc2[K + k] += (double)r2;
-                        }
-                    }
+                for (int k = 0; k < K; ++k) {
+                    const float rn = fmaf(-alpha[k], Q(li, k, row), R(li, k, row));
+                    R(li, k, row) = rn;
+                    const float r2 = rn * rn;
+                    acc2[k] += (double)(di * r2);
+                    acc2[K + k] += (double)r2;
                 }
             }
             if (prof) { const long long t1 = clock64(); tB += t1 - t0; t0 = t1; }
+            // phase C's first batch of global loads (own p rows and x) depends on neither alpha nor beta: issue it now so
+            // that its latency overlaps the all-reduce
+#pragma unroll
+            for (int j = 0; j < UBC; ++j) {
+                const int s = s_begin + warp + j * PWARPS;
+                if (PREFC && s < s_end) {
+                    const int row = s * 32 + lane;
+                    pc0[j] = ld_coherent4(a.p + 4 * (size_t)row);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) xc0[j][k] = a.x[(size_t)k * Vp + row];
+                }
+            }
             {
                 const int ns = S->nslot;
                 bool ok = false;
@@ -549,15 +551,33 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
         if (S->stop) break;
         // ---------------- phase C: p = D^-1 r + beta p, then make p visible
         {
-            float beta[K];
+            float beta[K], alpha[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) beta[k] = S->beta[k];
+            for (int k = 0; k < K; ++k) {
+                beta[k] = S->beta[k];
+                alpha[k] = S->alpha[k];
+            }
             for (int sb = s_begin + warp; sb < s_end; sb += UBC * PWARPS) {
                 float4 po[UBC];
+                float xo[UBC][K];
+                if (PREFC && sb == s_begin + warp) {          // first batch was loaded before the all-reduce
 #pragma unroll
-                for (int j = 0; j < UBC; ++j) {
-                    const int s = sb + j * PWARPS;
-                    if (s < s_end) po[j] = ld_coherent4(a.p + 4 * (size_t)(s * 32 + lane));
+                    for (int j = 0; j < UBC; ++j) {
+                        po[j] = pc0[j];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) xo[j][k] = xc0[j][k];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < UBC; ++j) {      // all global loads of UBC owned slices in flight together
+                        const int s = sb + j * PWARPS;
+                        if (s < s_end) {
+                            const int row = s * 32 + lane;
+                            po[j] = ld_coherent4(a.p + 4 * (size_t)row);
+#pragma unroll
+                            for (int k = 0; k < K; ++k) xo[j][k] = a.x[(size_t)k * Vp + row];
+                        }
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < UBC; ++j) {
@@ -567,7 +587,10 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
                         const float di = RES ? d_s[(size_t)li * 32 + lane] : a.dinv[row];
                         float pn[4] = {po[j].x, po[j].y, po[j].z, po[j].w};
 #pragma unroll
-                        for (int k = 0; k < K; ++k) pn[k] = fmaf(beta[k], pn[k], di * R(li, k, row));
+                        for (int k = 0; k < K; ++k) {
+                            a.x[(size_t)k * Vp + row] = fmaf(alpha[k], pn[k], xo[j][k]);     // x += alpha p (this iteration's p)
+                            pn[k] = fmaf(beta[k], pn[k], di * R(li, k, row));               // p = D^-1 r + beta p
+                        }
                         *reinterpret_cast<float4 *>(a.p + 4 * (size_t)row) = make_float4(pn[0], pn[1], pn[2], pn[3]);
                     }
                 }
@@ -590,12 +613,21 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
     }
 
     // ------------------------------------------------------------------ result: x (planes) -> caller layout
-    for (int s = s_begin + warp; s < s_end; s += PWARPS) {
-        const int row = s * 32 + lane;
-        if (row < a.V) {
-            const long long io = a.perm ? a.perm[row] : row;
+    // the last iteration's x += alpha p is still pending (it lives in phase C, which the stopping iteration skips)
+    {
+        const bool pending = S->it > 0;
+        float alpha[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) a.out[io * K + k] = a.x[(size_t)k * Vp + row];
+        for (int k = 0; k < K; ++k) alpha[k] = pending ? S->alpha[k] : 0.f;
+        for (int s = s_begin + warp; s < s_end; s += PWARPS) {
+            const int row = s * 32 + lane;
+            if (row < a.V) {
+                const long long io = a.perm ? a.perm[row] : row;
+                const float4 po = ld_coherent4(a.p + 4 * (size_t)row);
+                const float pk[4] = {po.x, po.y, po.z, po.w};
+#pragma unroll
+                for (int k = 0; k < K; ++k) a.out[io * K + k] = fmaf(alpha[k], pk[k], a.x[(size_t)k * Vp + row]);
+            }
         }
     }
     if (cta == 0 && tid == 0 && a.info) {

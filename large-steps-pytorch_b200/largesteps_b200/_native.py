@@ -10,7 +10,7 @@ from ctypes import c_int, c_int64, c_uint64, c_size_t, c_float, c_void_p, c_char
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libls_b200.so")
+LIB_PATH = os.environ.get("LS_LIB_PATH") or os.path.join(_HERE, "libls_b200.so")   # LS_LIB_PATH: A/B builds while tuning
 
 LS_OK, LS_ERR_BAD_ARG, LS_ERR_CUDA, LS_ERR_BREAKDOWN, LS_ERR_NOT_CONVERGED, LS_ERR_UNSUPPORTED, \
     LS_ERR_INDEX_RANGE, LS_ERR_WORKSPACE = range(8)
