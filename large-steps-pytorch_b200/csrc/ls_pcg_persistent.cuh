@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
     constexpr int U = 8;
     constexpr int UBC = 3;    // owned slices whose global loads are in flight together in phase C
 #ifndef LS_PREFC
-#define LS_PREFC 1
+#define LS_PREFC 0   // measured: the live registers across the reduction cost more (spills) than the overlap gains (2.61 vs 3.01 ms)
 #endif
     constexpr bool PREFC = (LS_PREFC != 0);   // prefetch phase C's first batch across all-reduce 2
 
