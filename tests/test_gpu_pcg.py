@@ -332,6 +332,37 @@ def test_full_size_roundtrip_adjoint_linearity():
     assert rel_l2(x2.cpu().numpy(), (2.0 * x + y).cpu().numpy()) < BAR
 
 
+def test_config4_batch_of_meshes_one_rank():
+    """BASELINE config 4 (8 independent 250K-vertex meshes) on however many GPUs there are: mesh i -> rank i mod N
+    (distributed.assign); with one rank the same code walks all eight.  Round-trip property per mesh."""
+    from largesteps_b200 import distributed as D
+    mine = D.assign(8, D.rank(), D.world())
+    assert len(mine) == 8 // D.world()
+    for i in mine:
+        v, f = workloads.plane(500, seed=i)
+        tv, tf = to_dev(v, f)
+        M = compute_matrix(tv, tf, 1.0, alpha=0.95)
+        assert M._nnz() == 1746002
+        x = from_differential(M, to_differential(M, tv))
+        assert rel_l2(x.cpu().numpy(), v) < BAR
+        del M
+
+
+def test_quarter_million_cotangent_vs_direct():
+    """250K vertices, cotangent Laplacian, lambda = 19 against the fp64 direct solve (the largest size the CPU
+    factorisation finishes in seconds)."""
+    v, f = workloads.plane(500, seed=3)
+    kw = dict(lambda_=19.0, cotan=True)
+    (r, c, val, V), ds = direct_for(v, f, kw)
+    _, b, g = rhs(r, c, val, V, v)
+    M = compute_matrix(*to_dev(v, f), **kw)
+    u = t(b).requires_grad_(True)
+    x = from_differential(M, u)
+    (x * t(g)).sum().backward()
+    assert rel_l2(x.detach().cpu().numpy(), ds.solve(b)) < BAR
+    assert rel_l2(u.grad.cpu().numpy(), ds.solve(g)) < BAR
+
+
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpus_independent_meshes():
     """Config 4 in miniature: one mesh per GPU, solved independently (no collective on the solve path)."""
