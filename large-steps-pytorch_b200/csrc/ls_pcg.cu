@@ -785,7 +785,15 @@ int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int max
         fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, true> : (const void *)lsp::pcg_persistent_kernel<3, 0, true>;
         LS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->persist_smem));
     }
-    LS_CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(h->persist_grid), dim3(lsp::PT), params, h->persist_smem, stream));
+    cudaError_t ce = cudaLaunchCooperativeKernel(fn, dim3(h->persist_grid), dim3(lsp::PT), params, h->persist_smem, stream);
+    if (ce != cudaSuccess) {
+        // e.g. the device is partitioned (MPS / MIG limits) and cannot co-schedule the grid: not fatal, the graph-mode
+        // solver computes the same thing; remember the failure so later solves go there directly
+        cudaGetLastError();
+        h->persist_on = 0;
+        ls_set_error("cooperative launch of the persistent solver failed (%s); using the graph-mode solver", cudaGetErrorString(ce));
+        return -1;
+    }
     g_ls_launches.fetch_add(1, std::memory_order_relaxed);
     return finish_info(h, rtol, maxit, a.info, info_host, stream);
 }
@@ -793,8 +801,10 @@ int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int max
 template <int K>
 int solve_k(PcgHandle *h, const float *b, float *x, const float *x0, float rtol, int maxit, float *info_dev,
             float *info_host, cudaStream_t stream) {
-    if (K == 3 && h->persist_on && x0 == nullptr)
-        return solve_persistent(h, b, x, rtol, maxit, info_dev, info_host, stream, false);
+    if (K == 3 && h->persist_on && x0 == nullptr) {
+        const int prc = solve_persistent(h, b, x, rtol, maxit, info_dev, info_host, stream, false);
+        if (prc != -1) return prc;     // -1: cooperative launch refused, fall through to the graph-mode solver
+    }
     int occ;
     int rc = lsk::spmm_prepare(K, true, h->cfg, &occ);
     if (rc) return rc;
@@ -810,8 +820,10 @@ int solve_k(PcgHandle *h, const float *b, float *x, const float *x0, float rtol,
         LS_LAUNCH_CHECK();
         k_init<K, false><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, b, rtol, maxit, 1);   // runs only if `restart`
         LS_LAUNCH_CHECK();
-        if (K == 3 && h->persist_on)   // iterate in the persistent kernel from the state the three kernels above left
-            return solve_persistent(h, b, x, rtol, maxit, info_dev, info_host, stream, true);
+        if (K == 3 && h->persist_on) {   // iterate in the persistent kernel from the state the three kernels above left
+            const int prc = solve_persistent(h, b, x, rtol, maxit, info_dev, info_host, stream, true);
+            if (prc != -1) return prc;
+        }
     } else {
         k_init<K, false><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, b, rtol, maxit, 0);
         LS_LAUNCH_CHECK();

@@ -31,7 +31,7 @@ else:
     kw = dict(lambda_=1.0, alpha=0.95)
 tv, tf = torch.from_numpy(v).to(dev), torch.from_numpy(f).to(dev)
 M = compute_matrix(tv, tf, **kw)
-hs = [PCGSolver(M, reorder=os.environ.get('PROBE_REORDER', '1') == '1') for _ in range(4)]
+hs = [PCGSolver(M, reorder=os.environ.get('PROBE_REORDER', '1') == '1') for _ in range(int(os.environ.get('PROBE_HANDLES', '4')))]
 u = to_differential(M, tv + 0.01 * torch.randn_like(tv))
 
 
