@@ -47,9 +47,13 @@ class PCGSolver(Solver):
     strict : bool    raise NotConverged if maxit is reached (otherwise warn and return the last iterate)
     reorder : bool   let the solver re-order its private matrix copy along the Morton curve recorded by
                      compute_matrix (pure data-layout change: b and x stay in the caller's vertex numbering)
+    check : bool     True: every solve synchronises, raises Breakdown / NotConverged (or warns).  False: the solve is
+                     fully asynchronous on the current stream (one kernel launch, no host round trip); status and
+                     iteration count are read lazily (`.iterations`, `.status`, `.raise_for_status()`).
     """
 
-    def __init__(self, M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, strict=False, reorder=True):
+    def __init__(self, M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, strict=False, reorder=True,
+                 check=True):
         if precond not in ("jacobi", "none"):
             raise ValueError(f"Unknown preconditioner '{precond}'.")
         rowptr, col, val = csr_of(M)
@@ -61,9 +65,12 @@ class PCGSolver(Solver):
         self.maxit = int(maxit)
         self.warm_start = bool(warm_start)
         self.strict = bool(strict)
+        self.check = bool(check)
         self.guess_fwd = None
         self.guess_bwd = None
         self._info_host = (ctypes.c_float * 8)()
+        self._info_dev = None        # device-side info of the last asynchronous solve
+        self._info_stale = False
         self._handle = ctypes.c_void_p(0)
         lib = N.lib()
         with torch.cuda.device(self.device):
@@ -84,13 +91,35 @@ class PCGSolver(Solver):
             self._handle = ctypes.c_void_p(0)
 
     # -- stats of the last solve ------------------------------------------------------------------------
+    def _sync_info(self):
+        if self._info_stale:     # asynchronous solve: fetch [iterations, status, relres...] now (synchronises)
+            host = self._info_dev.cpu()
+            for j in range(8):
+                self._info_host[j] = float(host[j])
+            self._info_stale = False
+
     @property
     def iterations(self):
+        self._sync_info()
         return int(self._info_host[0])
 
     @property
     def relres(self):
+        self._sync_info()
         return [float(self._info_host[2 + j]) for j in range(4)]
+
+    @property
+    def status(self):
+        """0/1 converged, 2 iteration cap reached, 3 breakdown (not SPD / NaN) -- of the last solve."""
+        self._sync_info()
+        return int(self._info_host[1])
+
+    def raise_for_status(self):
+        st = self.status
+        if st == 3:
+            raise N.Breakdown(f"CG breakdown after {self.iterations} iterations (matrix not SPD or NaN in the right-hand side)")
+        if st == 2:
+            raise N.NotConverged(f"PCG did not reach rtol={self.rtol} within maxit={self.maxit} (relres {self.relres})")
 
     def describe(self):
         out = (ctypes.c_int64 * 8)()
@@ -147,12 +176,20 @@ class PCGSolver(Solver):
                     bb = b[:, k0:k0 + kk].contiguous()
                     xx = torch.empty_like(bb)
                     gg = x0[:, k0:k0 + kk].contiguous() if x0 is not None else None
-                rc = lib.ls_pcg_solve(self._handle, N.ptr(bb), N.ptr(xx), N.ptr(gg), kk, self.rtol, self.maxit,
-                                      None, self._info_host, st)
-                if rc == N.LS_ERR_NOT_CONVERGED and not self.strict:
-                    warnings.warn(f"{type(self).__name__}: {N.last_error()}", RuntimeWarning)
+                if self.check:
+                    rc = lib.ls_pcg_solve(self._handle, N.ptr(bb), N.ptr(xx), N.ptr(gg), kk, self.rtol, self.maxit,
+                                          None, self._info_host, st)
+                    self._info_stale = False
+                    if rc == N.LS_ERR_NOT_CONVERGED and not self.strict:
+                        warnings.warn(f"{type(self).__name__}: {N.last_error()}", RuntimeWarning)
+                    else:
+                        N.check(rc, "ls_pcg_solve")
                 else:
-                    N.check(rc, "ls_pcg_solve")
+                    if self._info_dev is None:
+                        self._info_dev = torch.zeros(8, dtype=torch.float32, device=self.device)
+                    N.check(lib.ls_pcg_solve(self._handle, N.ptr(bb), N.ptr(xx), N.ptr(gg), kk, self.rtol, self.maxit,
+                                             N.ptr(self._info_dev), None, st), "ls_pcg_solve")
+                    self._info_stale = True
                 if k > K_MAX:
                     x[:, k0:k0 + kk] = xx
         if self.warm_start:
@@ -174,10 +211,12 @@ def bench_kernels(solvers, which, launches, k=3):
 
 class CholeskySolver(PCGSolver):
     """Drop-in for the reference CholeskySolver (solvers.py:26-39).  No factorisation happens: the system is
-    solved by the device PCG from a cold start to a relative residual of 1e-7 (<= 1e-5 rel-L2 of a direct solve)."""
+    solved by the device PCG from a cold start to a relative residual of 1e-7 (<= 1e-5 rel-L2 of a direct solve).
+    One asynchronous kernel launch per solve (`check=False`); `.raise_for_status()` checks the last solve on demand."""
 
     def __init__(self, M):
-        super().__init__(M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False)
+        # like cholespy's solve, the call is asynchronous and has no failure path: NaN in -> NaN out
+        super().__init__(M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, check=False)
 
 
 class ConjugateGradientSolver(PCGSolver):

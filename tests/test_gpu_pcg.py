@@ -273,6 +273,31 @@ def test_failure_modes():
         s.solve(torch.zeros(V + 1, 3, device=DEV))
 
 
+def test_asynchronous_solve_and_lazy_status():
+    """CholeskySolver (what from_differential uses by default) launches one kernel and returns without a host round
+    trip, like cholespy; status and iteration count are fetched on demand."""
+    v, f = workloads.icosphere(3)
+    (r, c, val, V), ds = direct_for(v, f, dict(lambda_=10.0))
+    M = compute_matrix(*to_dev(v, f), 10.0)
+    s = CholeskySolver(M)
+    assert s.check is False
+    b = np.random.default_rng(0).normal(size=(V, 3)).astype(np.float32)
+    x = s.solve(t(b))
+    assert s.status in (0, 1) and 0 < s.iterations < 500
+    s.raise_for_status()
+    assert rel_l2(x.cpu().numpy(), ds.solve(b)) < BAR
+    bad = t(b).clone()
+    bad[3, 0] = float("nan")
+    s.solve(bad)                    # no exception here (the reference has no failure path either) ...
+    assert s.status == 3
+    with pytest.raises(N.Breakdown):
+        s.raise_for_status()        # ... the failure is reported on demand
+    capped = PCGSolver(M, maxit=2, check=False)
+    capped.solve(t(b))
+    with pytest.raises(N.NotConverged):
+        capped.raise_for_status()
+
+
 def test_solver_cache_semantics():
     v, f = workloads.icosphere(2)
     M = compute_matrix(*to_dev(v, f), 10.0)
