@@ -205,9 +205,10 @@ def run_b200(args, wl, wl_name):
     V = v.shape[0]
     tv = torch.from_numpy(v).to(dev)
     tf = torch.from_numpy(f).to(dev)
+    M = compute_matrix(tv, tf, **kw)              # first call pays library / context warm-up
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    M = compute_matrix(tv, tf, **kw)
+    M = compute_matrix(tv, tf, **kw)              # steady-state assembly time (what a re-parameterisation after remesh costs)
     torch.cuda.synchronize()
     t_assemble = time.perf_counter() - t0
     nnz = M._nnz()
@@ -395,7 +396,17 @@ def run_b200(args, wl, wl_name):
         best = min(cb["t_solve_s"])
         parity = float(np.linalg.norm(xs.cpu().numpy().astype(np.float64) - cb["solver"].solve(b_host[0]).astype(np.float64))
                        / np.linalg.norm(cb["x_last"].astype(np.float64)))
+        # the reference's other plug-in (ConjugateGradientSolver, solvers.py:41-126) restated in numpy fp32, one solve
+        import oracle as _o
+        t0c = time.perf_counter()
+        rc_ = _o.compute_matrix(v, f, **kw)
+        cgp = _o.ReferenceCG(rc_[0], rc_[1], rc_[2], rc_[3])
+        t0c = time.perf_counter()
+        cgp.solve(b_host[0])
+        t_cg = time.perf_counter() - t0c
         cpu = {"value": 1.0 / best, "unit": "solves/s", "cores": 1, "kind": "port",
+               "reference_cg_port": {"solves_per_s": 1.0 / t_cg, "iterations_per_axis": cgp.iters,
+                                     "note": "numpy/scipy fp32 restatement of the reference CG (absolute tol 1e-5), 1 solve"},
                "sample": (f"{nsolve} direct solves (best of) of a (V,3) fp32 RHS at V={V} after an untimed "
                           f"{cb['t_factor_s']:.1f} s factorisation; scipy SuperLU symmetric mode = stand-in for the "
                           f"reference's cholespy/CHOLMOD CholeskySolver"),

@@ -774,9 +774,10 @@ int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int max
         // fast all-reduce slots this solve can touch: 2 per iteration (beyond the ring the kernel uses the slow path)
         long long need = 2LL * maxit + 8;
         if (need > h->ring_slots) need = h->ring_slots;
-        const char *e = getenv("LS_PCG_FASTRED");
+        const char *e = getenv("LS_PCG_FASTRED");   // "0": fenced all-reduce only; "N": at most N fast slots (tests the hand-over)
         a.ring = h->ring;
         a.ring_slots = (e && e[0] == '0') ? 0 : (h->persist_grid <= 255 ? (int)need : 0);
+        if (e && atoi(e) > 0 && atoi(e) < a.ring_slots) a.ring_slots = atoi(e);
         if (a.ring_slots > 0) LS_CUDA_TRY(cudaMemsetAsync(h->ring, 0, (size_t)a.ring_slots * 64, stream));
     }
     void *params[] = {(void *)&a};

@@ -15,6 +15,7 @@ Differences worth knowing: the device is taken from `verts`
 an isolated vertex gets an explicit 0 on the diagonal of a bare Laplacian (compute_matrix is identical: identity row).
 """
 import ctypes
+import warnings
 import weakref
 
 import torch
@@ -121,7 +122,9 @@ def _assemble(verts, faces, shift, scale, cotan):
                                      float(shift), float(scale), N.ptr(ws), nbytes.value, nnz,
                                      N.ptr(idx[0]), N.ptr(idx[1]), N.ptr(val),
                                      N.ptr(rowptr), N.ptr(col), N.ptr(val), st), "ls_assemble_fill")
-    M = torch.sparse_coo_tensor(idx, val, (V, V), is_coalesced=True, check_invariants=False)
+    with warnings.catch_warnings():      # torch warns once that invariant checks are off; the kernel guarantees them
+        warnings.simplefilter("ignore")
+        M = torch.sparse_coo_tensor(idx, val, (V, V), is_coalesced=True, check_invariants=False)
     # the solver re-orders its private copy of M along a Morton curve of the positions (the public M is untouched)
     order = morton_order(verts) if V >= ORDER_MIN_V else None
     _remember_csr(M, rowptr, col, val, order)

@@ -196,6 +196,7 @@ def test_morton_reorder_is_transparent(bunny_mesh):
     {},                                   # default: persistent kernel, r/Ap in shared memory, fixed-point all-reduce
     {"LS_PCG_RES": "0"},                  # persistent kernel, r/Ap in global memory
     {"LS_PCG_FASTRED": "0"},              # persistent kernel, fenced partial-array all-reduce
+    {"LS_PCG_FASTRED": "11"},             # fast all-reduce for 11 reductions, then the fenced one takes over mid-solve
     {"LS_PCG_MODE": "graph"},             # CUDA graph of 3 kernels per iteration, SELL SpMM engine
     {"LS_PCG_MODE": "graph", "LS_SPMM_ENGINE": "csr"},   # ... with the TMA-staged CSR SpMM engine
     {"LS_FORCE_REORDER": "1"},            # Morton re-ordered private copy
