@@ -1,22 +1,28 @@
-// ls_pcg.cu -- Jacobi-preconditioned conjugate gradients for M X = B, all K columns in one pass (sm_100a).
+// ls_pcg.cu -- Jacobi-preconditioned conjugate gradients for M X = B, all K columns in one pass (sm_100a):
+// handle / workspace management, the graph-mode solver and the C entry points.
 //
 // Replaces the reference's solve plug-ins (largesteps/solvers.py:26-39 CholeskySolver -> cholespy/CHOLMOD,
 // solvers.py:41-126 ConjugateGradientSolver -> ~12 eager torch kernels + 1 host sync per iteration per axis).
 //
-// Data layout in HBM (all inside the caller-provided workspace):
-//   CSR copy  rowptr (V+1) int32, col (nnz) int32, val (nnz) fp32, padded so 16-byte TMA granules never leave it
-//   dinv      Vp fp32                      Jacobi 1/diag (0 in the padding)
-//   x r p Ap  K planes of Vp fp32 each     SoA: plane k holds column k; Vp = V rounded up to 32 (zero padded)
-//   ctrl      PcgCtrl                      device-resident scalars: the iteration never returns to the host for them
+// Two execution modes share the handle, the data layout and the arithmetic:
+//   * persistent (ls_pcg_persistent.cuh): the whole solve is ONE cooperative kernel -- the default for K = 3;
+//   * graph (this file): one iteration = three kernels, a CUDA graph of CHUNK iterations replayed until a device-side
+//     `done` flag is seen -- the general fallback (K != 3, no cooperative launch) and the warm-start initialiser:
+//       K1  Ap = A p, pAp_k = p_k.Ap_k                     (SELL-32 or TMA-staged CSR SpMM + deterministic grid reduction)
+//       K2  x += a p; r -= a Ap; rz' = r.(dinv r); rr = r.r (fused update + 2K dot products; last CTA does the
+//           scalar state transition: beta, convergence per column, iteration count, done flag)
+//       K3  p = dinv r + beta p
 //
-// One iteration = three kernels, every global vector read/written once per kernel:
-//   K1  Ap = A p, pAp_k = p_k.Ap_k                     (TMA-staged SpMM + deterministic grid reduction)
-//   K2  x += a p; r -= a Ap; rz' = r.(dinv r); rr = r.r (fused update + 2K dot products; last CTA does the
-//       scalar state transition: beta, convergence per column, iteration count, done flag)
-//   K3  p = dinv r + beta p
+// Data layout in HBM (all inside the caller-provided workspace):
+//   CSR copy  rowptr (V+1) int32, col (nnz) int32, val (nnz) fp32, padded so 16-byte TMA granules never leave it;
+//             optionally re-ordered P A P^T (Morton order of the vertices, kept only if it gathers more coherently)
+//   SELL-32   soff (V/32+1), ent (padded nnz) int2 {col, val}: the fast SpMM engine's copy
+//   dinv      Vp fp32                      Jacobi 1/diag (0 in the padding)
+//   x r Ap    K planes of Vp fp32 each     SoA: plane k holds column k; Vp = V rounded up to 32 (zero padded)
+//   p         Vp rows of PW floats         PW = 1, 2, 4 for K = 1, 2, 3|4: a gather of p[col] is one load
+//   ctrl      PcgCtrl                      device-resident scalars: the iteration never returns to the host for them
 // Columns carry their own alpha/beta and freeze independently when ||r_k|| <= rtol ||b_k||, which is exactly the
 // reference's "one CG per axis" (solvers.py:115-118) run in lock-step.  Dot products accumulate in fp64.
-// The iteration loop is a CUDA graph of CHUNK iterations replayed until the device-side `done` flag is seen.
 #include <new>
 #include <string.h>
 #include <stdlib.h>
@@ -31,7 +37,7 @@ constexpr int VEC_THREADS = 256;
 constexpr int CHUNK = 8;   // CG iterations per graph launch
 
 struct PcgCtrl {
-    double rz[KMAX], rz_new[KMAX], pAp[KMAX], rr[KMAX], bb[KMAX];
+    double rz[KMAX], pAp[KMAX], rr[KMAX], bb[KMAX];
     float beta[KMAX];
     float rtol2;
     int maxit;
@@ -68,7 +74,6 @@ struct PcgHandle {
     int *scan;
     int has_perm;
     int planned;
-    int vec_mode;
     // SELL-32 engine (fast path)
     int *soff;
     int2 *ent;
@@ -349,7 +354,6 @@ __global__ void __launch_bounds__(VEC_THREADS) k_init(VecArgs a, const float *__
             // guard, solvers.py:107-110, and loses accuracy when the gradient scale changes between steps)
             if (WARM && tot[2 * K + k] > tot[K + k]) worse = 1;
             c->rz[k] = tot[k];
-            c->rz_new[k] = tot[k];
             c->bb[k] = tot[K + k];
             c->rr[k] = tot[2 * K + k];
             c->pAp[k] = 1.0;
@@ -441,7 +445,6 @@ __device__ __forceinline__ void pcg_transition(PcgCtrl *c, const double (&tot)[2
         const double rz_old = c->rz[k];
         c->beta[k] = (rz_old > 0.0) ? (float)(tot[k] / rz_old) : 0.f;
         c->rz[k] = tot[k];
-        c->rz_new[k] = tot[k];
         c->rr[k] = tot[K + k];
         const int cv = tot[K + k] <= (double)c->rtol2 * c->bb[k];
         c->conv[k] = cv;
@@ -453,66 +456,6 @@ __device__ __forceinline__ void pcg_transition(PcgCtrl *c, const double (&tot)[2
     if (bad) c->done = 3;
     else if (all) c->done = 1;
     else if (it >= c->maxit) c->done = 2;
-}
-
-// K2: x += alpha p, r -= alpha Ap, rz' = r.(dinv r), rr = r.r ; last CTA: scalar state transition.
-// One float4 per thread per column (grid sized to cover the planes in one pass when it fits); the vector loads are
-// issued BEFORE the dependent scalar chain (done flag -> pAp/rz -> fp64 divide) so that chain hides under them.
-template <int K>
-__global__ void __launch_bounds__(VEC_THREADS, 2) k_update(VecArgs a) {
-    __shared__ double red[2 * K * 32 + 2 * K + 1];
-    PcgCtrl *c = a.ctrl;
-    const int64_t n4 = a.Vp >> 2;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    float4 d, xv[K], pv[K], rv[K], qv[K];
-    auto load = [&](int64_t j) {
-        d = ld4(a.dinv + 4 * j);
-        load_p_rows<K>(a.p, j, pv);
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const size_t o = (size_t)k * a.Vp + 4 * j;
-            xv[k] = ld4(a.x + o);
-            rv[k] = ld4(a.r + o);
-            qv[k] = ld4(a.Ap + o);
-        }
-    };
-    if (i < n4) load(i);
-    if (!a.bench && *reinterpret_cast<volatile int *>(&c->done) != 0) return;
-    float alpha[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const double pAp = c->pAp[k];
-        alpha[k] = (c->conv[k] || !(pAp > 0.0)) ? 0.f : (float)(c->rz[k] / pAp);
-    }
-    double acc[2 * K];
-#pragma unroll
-    for (int q = 0; q < 2 * K; ++q) acc[q] = 0.0;
-    for (bool first = true; i < n4; i += stride, first = false) {
-        if (!first) load(i);
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const size_t o = (size_t)k * a.Vp + 4 * i;
-            const float al = alpha[k];
-            xv[k].x = fmaf(al, pv[k].x, xv[k].x);
-            xv[k].y = fmaf(al, pv[k].y, xv[k].y);
-            xv[k].z = fmaf(al, pv[k].z, xv[k].z);
-            xv[k].w = fmaf(al, pv[k].w, xv[k].w);
-            rv[k].x = fmaf(-al, qv[k].x, rv[k].x);
-            rv[k].y = fmaf(-al, qv[k].y, rv[k].y);
-            rv[k].z = fmaf(-al, qv[k].z, rv[k].z);
-            rv[k].w = fmaf(-al, qv[k].w, rv[k].w);
-            st4(a.x + o, xv[k]);
-            st4(a.r + o, rv[k]);
-            const float r2x = rv[k].x * rv[k].x, r2y = rv[k].y * rv[k].y, r2z = rv[k].z * rv[k].z, r2w = rv[k].w * rv[k].w;
-            acc[k] += (double)(d.x * r2x) + (double)(d.y * r2y) + (double)(d.z * r2z) + (double)(d.w * r2w);
-            acc[K + k] += (double)r2x + (double)r2y + (double)r2z + (double)r2w;
-        }
-    }
-    double tot[2 * K];
-    const bool last = ls_grid_reduce<2 * K>(acc, tot, a.partials, a.ticket, red, threadIdx.x, VEC_THREADS, 1,
-                                            blockIdx.x, gridDim.x);
-    if (last && threadIdx.x == 0 && !a.bench) pcg_transition<K>(c, tot);
 }
 
 // K3: p = dinv r + beta p   (same loads-first structure as K2)
@@ -548,9 +491,9 @@ __global__ void __launch_bounds__(VEC_THREADS, 4) k_pupdate(VecArgs a) {
     }
 }
 
-// Column-serial variants of K2 / K3: one column at a time per thread (4-5 float4 loads in flight instead of 13),
-// ~40 registers -> full occupancy.  Selected with LS_VEC_MODE=1 (sweeps); same arithmetic, same reduction order
-// per column, so results are bitwise identical to the fused-column variants.
+// K2: x += alpha p, r -= alpha Ap, rz' = r.(dinv r), rr = r.r ; last CTA: scalar state transition.
+// One float4 of rows per thread, one column at a time (4-5 float4 loads in flight, ~80 registers); the vector loads of
+// the first column are issued BEFORE the dependent scalar chain (done flag -> pAp/rz -> fp64 divide) so it hides under them.
 template <int K>
 __global__ void __launch_bounds__(VEC_THREADS, 3) k_update_cs(VecArgs a) {
     __shared__ double red[2 * K * 32 + 2 * K + 1];
@@ -694,8 +637,7 @@ template <int K>
 int launch_iteration(PcgHandle *h, cudaStream_t s) {
     int rc = launch_spmm<K>(h, true, s);
     if (rc) return rc;
-    if (h->vec_mode == 1) k_update_cs<K><<<h->vec_grid, VEC_THREADS, 0, s>>>(vec_args(h, 1));
-    else k_update<K><<<h->vec_grid, VEC_THREADS, 0, s>>>(vec_args(h, 1));
+    k_update_cs<K><<<h->vec_grid, VEC_THREADS, 0, s>>>(vec_args(h, 1));
     LS_LAUNCH_CHECK();
     k_pupdate<K><<<h->vec_grid, VEC_THREADS, 0, s>>>(vec_args(h, 1));
     LS_LAUNCH_CHECK();
@@ -985,10 +927,7 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
 
     // launch geometry
     lsk::spmm_config(&h->cfg);
-    {
-        const char *e = getenv("LS_VEC_MODE");
-        h->vec_mode = e ? atoi(e) : 1;
-    }
+
     int occ = 1;
     rc = lsk::spmm_prepare(3, true, h->cfg, &occ);
     if (rc) return fail(rc);
@@ -1158,8 +1097,7 @@ int bench_one(PcgHandle *h, int which, cudaStream_t stream) {
     if (which == 0 || which == 3) rc = launch_spmm<K>(h, false, stream);
     if (rc) return rc;
     if (which == 1 || which == 3) {
-        if (h->vec_mode == 1) k_update_cs<K><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va);
-        else k_update<K><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va);
+        k_update_cs<K><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va);
         LS_LAUNCH_CHECK();
     }
     if (which == 2 || which == 3) {
