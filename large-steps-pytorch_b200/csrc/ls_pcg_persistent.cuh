@@ -23,7 +23,10 @@
 
 namespace lsp {
 
-constexpr int PT = 768;     // 24 warps: 85 registers per thread (1024 threads forced spills into the SpMM loop)
+#ifndef LS_PT
+#define LS_PT 768
+#endif
+constexpr int PT = LS_PT;   // 24 warps: 85 registers per thread (1024 threads forced spills into the SpMM loop)
 constexpr int PWARPS = PT / 32;
 constexpr int NVMAX = 12;
 
@@ -249,7 +252,10 @@ __global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs
     const int s_end = (int)((long long)a.nslices * (cta + 1) / G);
     const long long Vp = a.Vp;
     constexpr int U = 8;
-    constexpr int UBC = 3;    // owned slices whose global loads are in flight together in phase C
+#ifndef LS_UBC
+#define LS_UBC 1   // A/B on B200 (profiles/r01_persistent_ab_threads_unroll.jsonl): 1 -> 2.40 ms, 2 -> 2.51, 3 -> 2.62, 4 -> 2.86 (spills)
+#endif
+    constexpr int UBC = LS_UBC;    // owned slices whose global loads are in flight together in phase C
 #ifndef LS_PREFC
 #define LS_PREFC 0   // measured: the live registers across the reduction cost more (spills) than the overlap gains (2.61 vs 3.01 ms)
 #endif
