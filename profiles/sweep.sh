@@ -1,10 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-run() { env "$@" timeout 300 python profiles/spmm_probe.py 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(json.dumps({k:d[k] for k in ('env','solve_ms','iters','us_per_iter') if k in d}))"; }
-D=$PWD/large-steps-pytorch_b200/largesteps_b200
+run() { env "$@" timeout 300 python profiles/spmm_probe.py 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(json.dumps({k:d[k] for k in ('env','spmm_cold_us','spmm_hot_us','solve_ms','iters','us_per_iter','phase_cycles_per_iter') if k in d}))"; }
 {
 run PROBE_MESH=plane
-for v in a b c d e; do run PROBE_MESH=plane LS_LIB_PATH=$D/libls_b200_$v.so; done
+run PROBE_MESH=plane LS_PCG_PROFILE=1
 run PROBE_MESH=bunny
-run PROBE_MESH=bunny LS_LIB_PATH=$D/libls_b200_e.so
-} | tee gpurun_out/sweep14.jsonl
+} | tee gpurun_out/sweep15.jsonl
