@@ -12,6 +12,8 @@ Parity pinning status
   * assembly (`geometry.py:3-133`), reference CG (`solvers.py:41-126`), AdamUniform (`optimize.py:17-41`),
     to_differential (`parameterize.py:30`): PINNED against outputs of the unmodified reference run in the
     builder container (tests/golden/make_golden.py -> tests/golden/*.npz; checked by tests/test_oracle.py).
+  * oracle/cg_port.c (+ cport.py): the reference CG once more in plain C with OpenMP, pinned against the same golden
+    outputs (tests/test_oracle.py); it is the multi-threaded CPU baseline of bench.py.
   * Cholesky path (`solvers.py:26-39`): the arithmetic lives in the third-party wheel `cholespy`
     (requirements.txt:1 `cholespy>=0.1.4`, not vendored, not installable offline) -- PARITY UNPINNED at that
     boundary.  It is a direct solve of M x = b, so the oracle is an fp64 sparse direct solve (SuperLU,
@@ -21,3 +23,4 @@ from .assembly import laplacian_uniform, laplacian_cot, compute_matrix, coo_to_s
 from .solve import (DirectSolver, dense_cholesky_solve, reference_cg, ReferenceCG,     # noqa: F401
                     to_differential, jacobi_pcg_f32)
 from .adam import AdamUniformOracle  # noqa: F401
+# oracle.cport.CPortCG: OpenMP C restatement of the reference CG (oracle/cg_port.c), built on demand with gcc
