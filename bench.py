@@ -161,7 +161,9 @@ def run_reference(args, wl, wl_name):
     rng = np.random.default_rng(100)
     bs = [(A @ (v + rng.normal(0, 0.01, v.shape).astype(np.float32))).astype(np.float32) for _ in range(2)]
     cg = CPortCG(r, c, val, V)
-    cg.solve(bs[1])                       # untimed: OpenMP thread pool start-up and first-touch page faults
+    cg.autotune_threads(bs[1])            # untimed: the thread count that actually runs fastest under this box's CPU quota
+    cg.guess_fwd = None
+    cg.solve(bs[1])                       # untimed: first-touch page faults
     cg.guess_fwd = None
     t0 = time.perf_counter()
     cg.solve(bs[0])
@@ -423,7 +425,9 @@ def run_b200(args, wl, wl_name):
         import oracle as _o
         rc_ = _o.compute_matrix(v, f, **kw)
         cgp = CPortCG(rc_[0], rc_[1], rc_[2], rc_[3])
-        cgp.solve(b_host[1])              # untimed: OpenMP thread pool start-up and first-touch page faults
+        cgp.autotune_threads(b_host[1])   # untimed: the thread count that actually runs fastest under this box's CPU quota
+        cgp.guess_fwd = None
+        cgp.solve(b_host[1])              # untimed: first-touch page faults
         t_cgs = []
         for _ in range(3):
             cgp.guess_fwd = None

@@ -27,6 +27,14 @@ int lsref_num_threads(void) {
 #endif
 }
 
+void lsref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* y = A x, CSR, fp32 (torch: `self.M @ p`, solvers.py:70,74) */
 static void spmv(int64_t n, const int32_t *rowptr, const int32_t *col, const float *val, const float *x, float *y) {
 #pragma omp parallel for schedule(static)

@@ -31,6 +31,7 @@ def lib():
     if _lib is None:
         h = ctypes.CDLL(build())
         h.lsref_num_threads.restype = ctypes.c_int
+        h.lsref_set_num_threads.argtypes = [ctypes.c_int]
         h.lsref_cg_solve.restype = ctypes.c_int
         h.lsref_cg_solve.argtypes = [ctypes.c_int64, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_float, ctypes.c_int,
                                                                                             ctypes.c_void_p]
@@ -52,6 +53,37 @@ class CPortCG:
         self.guess_bwd = None
         self.iters = []
         self.threads = lib().lsref_num_threads()
+
+    def autotune_threads(self, b, probe_iters=3):
+        """Pick the OpenMP thread count that runs a few CG iterations fastest.  The default (one thread per logical CPU)
+        can be far from it: under a cgroup CPU quota 128 threads on a 16-core allowance run 500x slower than 16."""
+        import time
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = os.cpu_count() or 1
+        cands = [t for t in (1, 2, 4, 8, 16, 24, 32, 48, 64, 96, 128, 192, 256) if t <= ncpu] or [1]
+        save = (self.guess_fwd, self.guess_bwd)
+        best_t, best_dt, worse = cands[0], float("inf"), 0
+        for t in cands:
+            lib().lsref_set_num_threads(t)
+            self.guess_fwd = None
+            self.solve(b, maxit=1)                     # thread pool start-up at this size
+            self.guess_fwd = None
+            t0 = time.perf_counter()
+            self.solve(b, maxit=probe_iters)
+            dt = time.perf_counter() - t0
+            if dt < best_dt:
+                best_t, best_dt, worse = t, dt, 0
+            else:
+                worse += 1
+                if worse >= 2:
+                    break
+        lib().lsref_set_num_threads(best_t)
+        self.threads = best_t
+        self.guess_fwd, self.guess_bwd = save
+        self.iters = []
+        return best_t
 
     def solve(self, b, backward=False, tol=1e-5, maxit=100000):
         b = np.ascontiguousarray(b, dtype=np.float32)
