@@ -54,7 +54,7 @@ class CPortCG:
         self.iters = []
         self.threads = lib().lsref_num_threads()
 
-    def autotune_threads(self, b, probe_iters=3):
+    def autotune_threads(self, b, probe_iters=8):
         """Pick the OpenMP thread count that runs a few CG iterations fastest.  The default (one thread per logical CPU)
         can be far from it: under a cgroup CPU quota 128 threads on a 16-core allowance run 500x slower than 16."""
         import time
@@ -69,10 +69,12 @@ class CPortCG:
             lib().lsref_set_num_threads(t)
             self.guess_fwd = None
             self.solve(b, maxit=1)                     # thread pool start-up at this size
-            self.guess_fwd = None
-            t0 = time.perf_counter()
-            self.solve(b, maxit=probe_iters)
-            dt = time.perf_counter() - t0
+            dt = float("inf")
+            for _ in range(2):                         # best of two: shared hosts are noisy
+                self.guess_fwd = None
+                t0 = time.perf_counter()
+                self.solve(b, maxit=probe_iters)
+                dt = min(dt, time.perf_counter() - t0)
             if dt < best_dt:
                 best_t, best_dt, worse = t, dt, 0
             else:
