@@ -88,7 +88,7 @@ struct PcgHandle {
     long long *dbg;
     unsigned long long *ring;
     int ring_slots;
-    int persist_on, persist_grid, persist_res, persist_nsl_max;
+    int persist_on, persist_grid, persist_res, persist_nsl_max, persist_threads;
     size_t persist_smem;
     // graphs, one per K
     cudaGraphExec_t graph[KMAX + 1];
@@ -723,12 +723,13 @@ int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int max
         if (a.ring_slots > 0) LS_CUDA_TRY(cudaMemsetAsync(h->ring, 0, (size_t)a.ring_slots * 64, stream));
     }
     void *params[] = {(void *)&a};
-    const void *fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, false> : (const void *)lsp::pcg_persistent_kernel<3, 0, false>;
-    if (a.dbg) {   // profiling build of the same kernel (LS_PCG_PROFILE): per-phase cycle counters in CTA 0
-        fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, true> : (const void *)lsp::pcg_persistent_kernel<3, 0, true>;
+    const void *fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, false, lsp::PWARPS> : (const void *)lsp::pcg_persistent_kernel<3, 0, false, lsp::PWARPS>;
+    if (h->persist_threads == lsp::PT_SMALL) fn = (const void *)lsp::pcg_persistent_kernel<3, 1, false, lsp::PT_SMALL / 32>;
+    else if (a.dbg) {   // profiling build of the same kernel (LS_PCG_PROFILE): per-phase cycle counters in CTA 0
+        fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, true, lsp::PWARPS> : (const void *)lsp::pcg_persistent_kernel<3, 0, true, lsp::PWARPS>;
         LS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->persist_smem));
     }
-    cudaError_t ce = cudaLaunchCooperativeKernel(fn, dim3(h->persist_grid), dim3(lsp::PT), params, h->persist_smem, stream);
+    cudaError_t ce = cudaLaunchCooperativeKernel(fn, dim3(h->persist_grid), dim3(h->persist_threads), params, h->persist_smem, stream);
     if (ce != cudaSuccess) {
         // e.g. the device is partitioned (MPS / MIG limits) and cannot co-schedule the grid: not fatal, the graph-mode
         // solver computes the same thing; remember the failure so later solves go there directly
@@ -1002,12 +1003,22 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
                 res = 0;
                 smem = lsp::persist_smem_bytes(3, 0, nsl_max);
             }
-            cudaError_t ce = res ? cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                 : cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t ce = res ? cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false, lsp::PWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                 : cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 0, false, lsp::PWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             int occ = 0;
             if (ce == cudaSuccess)
-                ce = res ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsp::pcg_persistent_kernel<3, 1, false>, lsp::PT, smem)
-                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsp::pcg_persistent_kernel<3, 0, false>, lsp::PT, smem);
+                ce = res ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsp::pcg_persistent_kernel<3, 1, false, lsp::PWARPS>, lsp::PT, smem)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsp::pcg_persistent_kernel<3, 0, false, lsp::PWARPS>, lsp::PT, smem);
+            h->persist_threads = lsp::PT;
+            const char *et = getenv("LS_PCG_SMALLCTA");
+            if (ce == cudaSuccess && occ >= 1 && res == 1 && g > 1 && nsl_max <= 16 && !(et && et[0] == '0')) {
+                // a CTA owns only a handful of slices: 8 warps are enough and make every CTA-level barrier cheaper
+                if (cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false, lsp::PT_SMALL / 32>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
+                    h->persist_threads = lsp::PT_SMALL;
+                else
+                    cudaGetLastError();
+            }
             if (ce == cudaSuccess && occ >= 1) {
                 h->persist_on = 1;
                 h->persist_grid = g;

@@ -28,6 +28,7 @@ namespace lsp {
 #endif
 constexpr int PT = LS_PT;   // 24 warps: 85 registers per thread (1024 threads forced spills into the SpMM loop)
 constexpr int PWARPS = PT / 32;
+constexpr int PT_SMALL = 256;   // CTAs that own <= 16 slices (mid-size meshes): cheaper CTA barriers, no spills
 constexpr int NVMAX = 12;
 
 struct GridBar {
@@ -119,7 +120,7 @@ __device__ __forceinline__ void allreduce_arrive(double (&v)[NV], double *partia
     if (warp == 0) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            const double s = ls_warp_sum(lane < PWARPS ? red[i * 32 + lane] : 0.0);
+            const double s = ls_warp_sum(lane < (int)(blockDim.x >> 5) ? red[i * 32 + lane] : 0.0);
             if (lane == 0) mine[(size_t)i * G + blockIdx.x] = s;
         }
     }
@@ -131,7 +132,7 @@ __device__ __forceinline__ void allreduce_finish(double (&v)[NV], double *partia
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     grid_wait(gb, gen, G);
     const double *mine = partials + (size_t)parity * NVMAX * G;
-    for (int i = warp; i < NV; i += PWARPS) {
+    for (int i = warp; i < NV; i += (int)(blockDim.x >> 5)) {
         const double *src = mine + (size_t)i * G;
         double s = 0.0;
         for (int c0 = 0; c0 < G; c0 += 256) {
@@ -195,7 +196,7 @@ __device__ __forceinline__ bool fast_allreduce(double (&v)[NV], const int *eref 
         double mine = 0.0;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            const double s = ls_warp_sum(lane < PWARPS ? red[i * 32 + lane] : 0.0);
+            const double s = ls_warp_sum(lane < (int)(blockDim.x >> 5) ? red[i * 32 + lane] : 0.0);
             if (lane == i) mine = s;
         }
         if (G == 1) {
@@ -234,9 +235,10 @@ __device__ __forceinline__ bool fast_allreduce(double (&v)[NV], const int *eref 
     return !poison;
 }
 
-template <int K, int RES, bool PROF>
-__global__ void __launch_bounds__(PT, 1) pcg_persistent_kernel(const PersistArgs a) {
+template <int K, int RES, bool PROF, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) pcg_persistent_kernel(const PersistArgs a) {
     static_assert(K == 3 || K == 4, "persistent kernel is instantiated for float4 p rows");
+    constexpr int PWARPS = NW;   // warps per CTA: 24 for large meshes, 8 when a CTA owns only a handful of slices
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *red = reinterpret_cast<double *>(smem_raw);                 // NV*32 + NV doubles (NV <= 8)
     Scal *S = reinterpret_cast<Scal *>(smem_raw + 3072);
