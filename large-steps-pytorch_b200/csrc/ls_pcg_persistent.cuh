@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_persistent_kernel(const Persis
     constexpr bool PREFC = (LS_PREFC != 0);   // prefetch phase C's first batch across all-reduce 2
 
     unsigned int gen = 0, parity = 0;   // gen = number of grid barriers passed (the host zeroes the counter per launch)
+    const long long ent_limit = a.soff[a.nslices];
 
     auto R = [&](int li, int k, int row) -> float & {
         return RES ? r_s[((size_t)li * K + k) * 32 + lane] : a.r[(size_t)k * Vp + row];
@@ -402,6 +403,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_persistent_kernel(const Persis
                 if (sn < s_end) {
                     n0 = a.soff[sn];
                     n1 = a.soff[sn + 1];
+                    if (sn + PWARPS < s_end) lsk::prefetch_entries_l2(a.ent, (long long)n0 + (n0 - o0), ent_limit, lane);
                 }
                 float acc[K];
 #pragma unroll

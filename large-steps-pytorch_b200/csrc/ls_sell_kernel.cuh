@@ -18,7 +18,10 @@
 
 namespace lsk {
 
-constexpr int SELL_THREADS = 768;   // one CTA per SM, 24 warps, <= 85 registers (same shape as the persistent solver's phase A)
+#ifndef LS_SELL_THREADS
+#define LS_SELL_THREADS 768
+#endif
+constexpr int SELL_THREADS = LS_SELL_THREADS;   // one CTA per SM, 24 warps, <= 85 registers (same shape as the persistent solver's phase A)
 constexpr int SELL_WARPS = SELL_THREADS / 32;
 
 struct SellArgs {
@@ -53,6 +56,19 @@ __device__ __forceinline__ int2 ld_entry(const int2 *p) {
     return r;
 }
 
+// L2 prefetch of the entries two slices ahead of this warp (the register prefetch covers one slice ahead): costs no
+// registers, turns the register prefetch's HBM miss into an L2 hit.  The address is extrapolated from the last two slice
+// offsets (slices of a mesh have near-constant width); a wrong guess only prefetches a neighbouring line.
+#ifndef LS_PF2
+#define LS_PF2 0   // A/B: no gain HBM-cold for the stand-alone kernel, and 2.66 vs 2.37 ms for the persistent solve (more spills)
+#endif
+__device__ __forceinline__ void prefetch_entries_l2(const int2 *ent, long long off, long long limit, int lane) {
+    if (LS_PF2 && off >= 0 && off + 256 <= limit) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) asm volatile("prefetch.global.L2 [%0];" ::"l"(ent + off + u * 32 + lane));
+    }
+}
+
 template <int K, bool DOT>
 __global__ void __launch_bounds__(SELL_THREADS, 1) spmm_sell_kernel(const SellArgs a) {
     typedef typename PRow<K>::T PT;
@@ -66,6 +82,7 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) spmm_sell_kernel(const SellAr
     const int s_begin = (int)((long long)a.nslices * cta / G);
     const int s_end = (int)((long long)a.nslices * (cta + 1) / G);
     const PT *__restrict__ prow = reinterpret_cast<const PT *>(a.p);
+    const long long limit = a.soff[a.nslices];
 
     double dacc[K];
 #pragma unroll
@@ -95,6 +112,7 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) spmm_sell_kernel(const SellAr
         if (sn < s_end) {
             n0 = a.soff[sn];
             n1 = a.soff[sn + 1];
+            if (sn + SELL_WARPS < s_end) prefetch_entries_l2(a.ent, (long long)n0 + (n0 - o0), limit, lane);
         }
         float acc[K];
 #pragma unroll
