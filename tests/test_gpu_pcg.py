@@ -358,6 +358,23 @@ def test_full_size_roundtrip_adjoint_linearity():
     assert rel_l2(x2.cpu().numpy(), (2.0 * x + y).cpu().numpy()) < BAR
 
 
+def test_four_million_vertices_roundtrip():
+    """Largest size exercised: plane 2000^2 (V = 4e6, nnz = 27,984,002).  r/Ap no longer fit in shared memory, so the
+    persistent kernel runs with them in global memory (RES = 0); round trip + true residual."""
+    v, f = workloads.plane(2000, seed=0)
+    tv, tf = to_dev(v, f)
+    M = compute_matrix(tv, tf, 1.0, alpha=0.95)
+    assert M._nnz() == 7 * 2000 * 2000 - 8 * 2000 + 2
+    s = PCGSolver(M)
+    assert s.describe()["persistent"] == 1
+    x = s.solve(to_differential(M, tv))
+    assert rel_l2(x.cpu().numpy(), v) < BAR
+    b = torch.randn(M.shape[0], 3, device=DEV)
+    y = s.solve(b)
+    res = (M @ y - b).norm(dim=0) / b.norm(dim=0)
+    assert float(res.max()) < 5e-6
+
+
 def test_config4_batch_of_meshes_one_rank():
     """BASELINE config 4 (8 independent 250K-vertex meshes) on however many GPUs there are: mesh i -> rank i mod N
     (distributed.assign); with one rank the same code walks all eight.  Round-trip property per mesh."""

@@ -136,3 +136,25 @@ def test_two_rank_gloo_sharding(tmp_path):
     for r in range(2):
         v, _ = workloads.plane(24, seed=r)
         assert np.linalg.norm(d["allx"][r] - v) / np.linalg.norm(v) < 1e-5
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints one JSON line with the contract's
+    keys; exercised on BASELINE config 1 so it finishes in seconds."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "icosphere",
+                          "--steps", "3", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "from_differential solves/sec @1M verts"
+    for key in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+                "data", "config", "cpu_baseline", "e2e"):
+        assert key in line
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"] == "icosphere"
+    # non-zero ranks of a torchrun launch exit quietly
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "icosphere",
+                          "--steps", "1"], capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
