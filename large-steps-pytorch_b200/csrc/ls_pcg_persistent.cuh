@@ -86,17 +86,19 @@ __device__ __forceinline__ void grid_arrive(GridBar *gb, unsigned int &gen, int 
     gen += 1u;
     if (G == 1) return;            // single-CTA solve: the CTA barrier is the grid barrier
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(&gb->count, 1u);
+        // release: every write this CTA made before the CTA barrier above is visible to whoever acquires the counter.
+        // (a plain __threadfence() here is a sequentially-consistent fence plus an L1 invalidate the arriving side has no use for)
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(&gb->count), "r"(1u) : "memory");
     }
 }
 __device__ __forceinline__ void grid_wait(GridBar *gb, unsigned int gen, int G) {
     if (G == 1) return;
     if (threadIdx.x == 0) {
         const unsigned int target = gen * (unsigned int)G;
+        // the acquire load pairs with the release above and invalidates this SM's L1 (CCTL.IVALL), so the plain loads the
+        // other threads issue after the CTA barrier below miss L1 and read the other CTAs' rows from L2
         while ((int)(ld_acquire(&gb->count) - target) < 0) {
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -170,6 +172,7 @@ struct Scal {                 // CTA-uniform solver scalars, kept in shared memo
     int e_rzrr[8];             // [rz | rr]
     int skipA[4], skipB[8];    // frozen columns contribute nothing
     int nslot;
+    int poison;
 };
 
 // ---- fast deterministic all-reduce: one 64-bit atomic per value, no fences, no second pass ------------------------------
@@ -182,9 +185,26 @@ struct Scal {                 // CTA-uniform solver scalars, kept in shared memo
 // and the CTAs that poll touch only that word, so nothing needs a fence: r, Ap and x are owner-only, and the only vector
 // other CTAs read (p) is published by the full barrier after phase C.  If any CTA poisons a value, every CTA sees the same
 // poison count and the whole grid repeats that reduction through the slow path.
-template <int NV>
+// binary exponent of a positive double straight from its bits (ilogb() is a function call); denormals / inf land outside
+// +-900 and are clamped by the user
+__device__ __forceinline__ int exp2_of(double d) { return (int)((__double_as_longlong(d) >> 52) & 0x7ff) - 1023; }
+
+// value `off + lane` of a register array without turning the array into an indexed (local-memory) one
+template <int KCOL, int N>
+__device__ __forceinline__ double pick_lane(const double (&v)[N], int off, int lane) {
+    double d = 0.0;
+#pragma unroll
+    for (int i = 0; i < KCOL; ++i) {
+        double t = v[off + i];
+        asm volatile("" : "+d"(t));
+        if (lane == i) d = t;
+    }
+    return d;
+}
+
+template <int NV, int KCOL, typename Post>
 __device__ __forceinline__ bool fast_allreduce(double (&v)[NV], const int *eref /* smem [NV] */, const int *skip /* smem [NV] */,
-                                               unsigned long long *slot, double *red, int G) {
+                                               unsigned long long *slot, double *red, int *poison_flag /* smem */, int G, Post post) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -193,23 +213,23 @@ __device__ __forceinline__ bool fast_allreduce(double (&v)[NV], const int *eref 
     }
     __syncthreads();
     if (warp == 0) {
-        double mine = 0.0;
+        double val = 0.0;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const double s = ls_warp_sum(lane < (int)(blockDim.x >> 5) ? red[i * 32 + lane] : 0.0);
-            if (lane == i) mine = s;
+            if (lane == i) val = s;
         }
-        if (G == 1) {
-            if (lane < NV) {
-                red[NV * 32 + lane] = mine;
-                red[NV * 32 + NV + lane] = 0.0;
-            }
-        } else if (lane < NV) {
-            const int e = eref[lane];
+        unsigned int pois = 0u;
+        if (G > 1 && lane < NV) {
+            // powers of two built from their bit patterns (ldexp() is a function call on the critical path); the exponent
+            // reference is clamped so that 2^(35-e) and 2^(e-35) stay normal numbers (-1000 marks "previous value was 0")
+            const int e = min(max(eref[lane], -900), 900);
+            const double up = __longlong_as_double((long long)(1023 + 35 - e) << 52);     // 2^(35-e)
+            const double down = __longlong_as_double((long long)(1023 + e - 35) << 52);   // 2^(e-35)
             unsigned long long word = 1ull;
             if (!skip[lane]) {
-                const bool fits = (mine == mine) && (fabs(mine) < ldexp(1.0, e + 3));
-                if (fits) word += ((unsigned long long)llrint(ldexp(mine, 35 - e))) << 16;
+                const bool fits = (val == val) && (fabs(val) * up < 274877906944.0 /* 2^38 */);
+                if (fits) word += ((unsigned long long)__double2ll_rn(val * up)) << 16;
                 else word += 1ull << 8;
             }
             atomicAdd(slot + lane, word);
@@ -217,22 +237,18 @@ __device__ __forceinline__ bool fast_allreduce(double (&v)[NV], const int *eref 
             do {
                 asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(slot + lane) : "memory");
             } while ((int)(w & 0xffull) != G);
-            red[NV * 32 + lane] = ldexp((double)((long long)w >> 16), e - 35);
-            red[NV * 32 + NV + lane] = (double)((w >> 8) & 0xffull);
+            val = (double)((long long)w >> 16) * down;
+            pois = (unsigned int)((w >> 8) & 0xffull);
         }
+        // the scalar bookkeeping that follows every reduction runs right here, on the warp that already holds the sums
+        // (one lane per column), instead of after another shared-memory round trip and two more CTA barriers
+        const bool poison = __any_sync(0xffffffffu, pois != 0u);
+        const double val2 = (NV > KCOL) ? __shfl_down_sync(0xffffffffu, val, KCOL) : 0.0;   // lane k: values k and KCOL + k
+        if (!poison) post(val, val2);
+        if (lane == 0) *poison_flag = poison ? 1 : 0;
     }
     __syncthreads();
-    bool poison = false;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        poison |= red[NV * 32 + NV + i] != 0.0;
-    }
-    if (!poison) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = red[NV * 32 + i];
-    }
-    __syncthreads();   // red[] is reused
-    return !poison;
+    return *poison_flag == 0;
 }
 
 template <int K, int RES, bool PROF, int NW>
@@ -456,24 +472,31 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_persistent_kernel(const Persis
             }
             if (prof) { const long long t1 = clock64(); tA += t1 - t0; t0 = t1; }
             {
+                // alpha_k = rz_k / pAp_k, one lane per column (executed by warp 0 only, with the full sums in t[])
+                auto postA = [&](const double d, const double) {
+                    bool bad = false;
+                    if (lane < K) {
+                        const bool conv = S->conv[lane] != 0, ok = d > 0.0;
+                        if (!conv && ok) S->e_pAp[lane] = exp2_of(d);
+                        bad = !conv && !ok;      // not SPD / NaN: finish this iteration's update with alpha = 0, then stop
+                        S->alpha[lane] = (conv || !ok) ? 0.f : (float)(S->rz[lane] / d);
+                    }
+                    const bool anybad = __any_sync(0xffffffffu, bad);
+                    if (lane == 0) {
+                        S->nslot += 1;
+                        if (anybad) S->status = 3;
+                    }
+                };
                 const int ns = S->nslot;
                 bool ok = false;
-                if (ns < a.ring_slots) ok = fast_allreduce<K>(dacc, S->e_pAp, S->skipA, a.ring + 8 * (size_t)ns, red, G);
-                if (!ok) grid_allreduce<K>(dacc, a.partials, a.bar, gen, parity, red, G);
-            }
-            if (tid == 0) {
-                S->nslot += 1;
-                for (int k = 0; k < K; ++k)
-                    if (!S->conv[k] && dacc[k] > 0.0 && dacc[k] == dacc[k]) S->e_pAp[k] = ilogb(dacc[k]);
-                int bad = 0;
-                for (int k = 0; k < K; ++k) {
-                    const bool ok = dacc[k] > 0.0;
-                    if (!S->conv[k] && !ok) bad = 1;
-                    S->alpha[k] = (S->conv[k] || !ok) ? 0.f : (float)(S->rz[k] / dacc[k]);
+                if (ns < a.ring_slots)
+                    ok = fast_allreduce<K, K>(dacc, S->e_pAp, S->skipA, a.ring + 8 * (size_t)ns, red, &S->poison, G, postA);
+                if (!ok) {
+                    grid_allreduce<K>(dacc, a.partials, a.bar, gen, parity, red, G);
+                    if (warp == 0) postA(pick_lane<K>(dacc, 0, lane), 0.0);
+                    __syncthreads();
                 }
-                if (bad) S->status = 3;     // not SPD / NaN: finish this iteration's update with alpha = 0, then stop
             }
-            __syncthreads();
             if (prof) { const long long t1 = clock64(); tR1 += t1 - t0; t0 = t1; }
         }
         // ---------------- phase B: r -= alpha Ap, r.z, r.r   (x += alpha p is folded into phase C)
@@ -514,48 +537,54 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_persistent_kernel(const Persis
                 }
             }
             {
+                // beta_k, convergence and the stop decision; one lane per column, lane 0 combines
+                auto postB = [&](const double rzn, const double rrn) {
+                    bool bad = false, cvk = true;
+                    if (lane < K) {
+                        if (S->conv[lane]) {
+                            S->beta[lane] = 0.f;
+                        } else {
+                            if (rzn > 0.0) S->e_rzrr[lane] = exp2_of(rzn);
+                            if (rrn > 0.0) S->e_rzrr[K + lane] = exp2_of(rrn);
+                            if (!(rzn == rzn)) bad = true;
+                            const double rz_old = S->rz[lane];
+                            float be = (rz_old > 0.0) ? (float)(rzn / rz_old) : 0.f;
+                            S->rz[lane] = rzn;
+                            S->rr[lane] = rrn;
+                            const double rtol2 = (double)a.rtol * (double)a.rtol;
+                            const bool cv = rrn <= rtol2 * S->bb[lane];
+                            S->conv[lane] = cv ? 1 : 0;
+                            if (cv) {
+                                be = 0.f;
+                                S->skipA[lane] = 1;
+                                S->skipB[lane] = S->skipB[K + lane] = 1;
+                            }
+                            S->beta[lane] = be;
+                            cvk = cv;
+                        }
+                    }
+                    const bool all = __all_sync(0xffffffffu, cvk);
+                    const bool anybad = __any_sync(0xffffffffu, bad);
+                    if (lane == 0) {
+                        S->nslot += 1;
+                        const int it = S->it + 1;
+                        S->it = it;
+                        if (anybad || S->status == 3) S->status = 3;
+                        else if (all) S->status = 1;
+                        else if (it >= a.maxit) S->status = 2;
+                        S->stop = S->status != 0;
+                    }
+                };
                 const int ns = S->nslot;
                 bool ok = false;
-                if (ns < a.ring_slots) ok = fast_allreduce<2 * K>(acc2, S->e_rzrr, S->skipB, a.ring + 8 * (size_t)ns, red, G);
-                if (!ok) grid_allreduce<2 * K>(acc2, a.partials, a.bar, gen, parity, red, G);
-            }
-            if (tid == 0) {
-                S->nslot += 1;
-                for (int k = 0; k < K; ++k) {
-                    if (S->conv[k]) continue;
-                    if (acc2[k] > 0.0 && acc2[k] == acc2[k]) S->e_rzrr[k] = ilogb(acc2[k]);
-                    if (acc2[K + k] > 0.0 && acc2[K + k] == acc2[K + k]) S->e_rzrr[K + k] = ilogb(acc2[K + k]);
+                if (ns < a.ring_slots)
+                    ok = fast_allreduce<2 * K, K>(acc2, S->e_rzrr, S->skipB, a.ring + 8 * (size_t)ns, red, &S->poison, G, postB);
+                if (!ok) {
+                    grid_allreduce<2 * K>(acc2, a.partials, a.bar, gen, parity, red, G);
+                    if (warp == 0) postB(pick_lane<K>(acc2, 0, lane), pick_lane<K>(acc2, K, lane));
+                    __syncthreads();
                 }
-                const double rtol2 = (double)a.rtol * (double)a.rtol;
-                int all = 1, bad = (S->status == 3);
-                for (int k = 0; k < K; ++k) {
-                    if (S->conv[k]) {
-                        S->beta[k] = 0.f;
-                        continue;
-                    }
-                    if (!(acc2[k] == acc2[k])) bad = 1;
-                    const double rz_old = S->rz[k];
-                    float be = (rz_old > 0.0) ? (float)(acc2[k] / rz_old) : 0.f;
-                    S->rz[k] = acc2[k];
-                    S->rr[k] = acc2[K + k];
-                    const int cv = acc2[K + k] <= rtol2 * S->bb[k];
-                    S->conv[k] = cv;
-                    if (cv) {
-                        be = 0.f;
-                        S->skipA[k] = 1;
-                        S->skipB[k] = S->skipB[K + k] = 1;
-                    }
-                    S->beta[k] = be;
-                    all &= cv;
-                }
-                const int it = S->it + 1;
-                S->it = it;
-                if (bad) S->status = 3;
-                else if (all) S->status = 1;
-                else if (it >= a.maxit) S->status = 2;
-                S->stop = S->status != 0;
             }
-            __syncthreads();
             if (prof) { const long long t1 = clock64(); tR2 += t1 - t0; t0 = t1; }
         }
         if (S->stop) break;
