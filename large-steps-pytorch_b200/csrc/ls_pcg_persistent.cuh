@@ -243,6 +243,7 @@ __device__ __forceinline__ bool fast_allreduce(double (&v)[NV], const int *eref 
         // the scalar bookkeeping that follows every reduction runs right here, on the warp that already holds the sums
         // (one lane per column), instead of after another shared-memory round trip and two more CTA barriers
         const bool poison = __any_sync(0xffffffffu, pois != 0u);
+        __syncwarp();   // lanes >= KCOL read eref[] / skip[] entries that post() rewrites from lanes < KCOL (racecheck)
         const double val2 = (NV > KCOL) ? __shfl_down_sync(0xffffffffu, val, KCOL) : 0.0;   // lane k: values k and KCOL + k
         if (!poison) post(val, val2);
         if (lane == 0) *poison_flag = poison ? 1 : 0;

@@ -26,8 +26,10 @@ for kw in (dict(lambda_=1.0, alpha=0.95), dict(lambda_=19.0, cotan=True)):
 torch.cuda.synchronize(); print("sanitizer case ok", os.environ.get("LS_PCG_MODE"), os.environ.get("LS_SPMM_ENGINE"))
 PY
 for tool in memcheck racecheck; do
-  for mode in "LS_PCG_MODE=persistent" "LS_PCG_MODE=graph" "LS_PCG_MODE=graph LS_SPMM_ENGINE=csr"; do
+  # SAN_QUICK=1: persistent mode only (after a change confined to ls_pcg_persistent.cuh)
+  for mode in "LS_PCG_MODE=persistent" ${SAN_QUICK:+--} "LS_PCG_MODE=graph" "LS_PCG_MODE=graph LS_SPMM_ENGINE=csr"; do
+    if [ "$mode" = "--" ]; then break; fi
     echo "=== $tool $mode"
-    env $mode timeout 600 compute-sanitizer --tool $tool --error-exitcode 7 python /tmp/san_case.py 2>&1 | grep -E "ERROR SUMMARY|sanitizer case ok|Error|hazard" | head -8
+    env $mode timeout 600 compute-sanitizer --tool $tool --error-exitcode 7 python /tmp/san_case.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitizer case ok|Error|hazard|access at" | head -12
   done
 done 2>&1 | tee gpurun_out/sanitizer.log
