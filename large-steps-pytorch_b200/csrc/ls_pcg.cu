@@ -82,7 +82,7 @@ struct PcgHandle {
     int nslices;
     int sell_on;
     int sell_grid;
-    // persistent single-kernel solve (K = 3, cold start)
+    // persistent single-kernel solve (K = 3; warm starts enter it in resume mode)
     lsp::GridBar *gbar;
     double *part_persist;
     long long *dbg;
@@ -983,7 +983,7 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
         h->sell_grid = (int)sg;
     }
     {
-        // persistent single-kernel solve: one 1024-thread CTA per SM, cooperative launch; r / Ap / dinv in shared memory
+        // persistent single-kernel solve: one 768-thread CTA per SM (256 for mid-size meshes), cooperative launch; r / Ap / dinv in shared memory
         // when the CTA's rows fit (RES = 1), in global memory otherwise (RES = 0)
         const char *e = getenv("LS_PCG_MODE");
         const bool want_graph = e && (e[0] == 'g' || e[0] == 'G');

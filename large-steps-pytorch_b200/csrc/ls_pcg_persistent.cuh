@@ -4,19 +4,21 @@
 // (a 48 MB p-update takes 10.3 us against 7.4 us of pure streaming), and r / Ap make a round trip through HBM between
 // kernels although only their owner thread ever touches them (profiles/r01_*).
 //
-// Structure: one CTA of 1024 threads per SM, launched cooperatively so that all CTAs are co-resident.  CTA c owns a
-// contiguous range of SELL-32 slices; warp w of the CTA owns slices s_begin + w + 32 i, lane l the row 32 s + l --
-// the SAME thread in every phase.  Per iteration:
+// Structure: one CTA of 768 threads per SM (256 when a CTA owns <= 16 slices), launched cooperatively so that all CTAs
+// are co-resident.  CTA c owns a contiguous range of SELL-32 slices; warp w of the CTA owns slices s_begin + w + NW i,
+// lane l the row 32 s + l -- the SAME thread in every phase.  Per iteration:
 //   phase A   Ap = A p for the owned rows (SELL entries streamed from HBM with register prefetch, p rows gathered
 //             through L1), p.Ap partial                                      -> grid all-reduce #1  (alpha)
-//   phase B   x += alpha p (x in global, owner-only), r -= alpha Ap, r.D^-1 r and r.r partials
-//                                                                           -> grid all-reduce #2  (beta, convergence)
-//   phase C   p = D^-1 r + beta p (p is the only vector other CTAs read)       -> grid barrier   #3  (p visible)
+//   phase B   r -= alpha Ap (shared memory only), r.D^-1 r and r.r partials    -> grid all-reduce #2  (beta, convergence)
+//   phase C   x += alpha p (owner-only, global), p = D^-1 r + beta p (p is the only vector other CTAs read)
+//                                                                           -> grid barrier   #3  (p visible)
 // r, Ap and D^-1 live in SHARED MEMORY for the whole solve when the CTA's rows fit (RES = 1: 28 B/row, 6784 rows/SM at
-// V = 1e6 = 190 KB of the 227 KB); otherwise (RES = 0) they stay in global memory.  The grid barrier is a
-// generation counter in global memory; the all-reduce writes per-CTA partials before arriving and every CTA re-reduces
-// them in the same fixed order afterwards, so the scalars are bit-identical on every CTA and run to run, and all CTAs
-// take the same convergence decision without another exchange.
+// V = 1e6 = 190 KB of the 227 KB); otherwise (RES = 0) they stay in global memory.
+// The two all-reduces are one 64-bit fixed-point atomic per value (fast_allreduce below): integer sums do not depend on
+// the arrival order, so the scalars are bit-identical on every CTA and run to run, and all CTAs take the same
+// convergence decision without another exchange.  The fallback (grid_allreduce: per-CTA partials, a fenced barrier, a
+// fixed-order re-reduction) has the same property and is used at start-up and whenever a partial does not fit the
+// fixed-point window.  The grid barrier is a monotone arrival counter (release add / acquire poll).
 #pragma once
 #include "ls_common.cuh"
 #include "ls_sell_kernel.cuh"
