@@ -74,3 +74,27 @@ def test_check_maps_status_to_exceptions():
     with pytest.raises(RuntimeError):
         N.check(N.LS_ERR_CUDA)
     N.check(N.LS_OK)
+
+
+def test_header_is_plain_c_and_the_c_host_example_links(tmp_path):
+    """include/largesteps_b200.h must be usable from C (the drop-in boundary is a C ABI, not a C++ or torch one):
+    the pure-C host example is compiled as strict C99 with -Wall -Wextra -Werror and linked against the library.
+    Nothing is executed here (no GPU); tests/test_gpu_integration_snippet.py runs it on the device."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h"):
+        pytest.skip("gcc or the CUDA headers are not available")
+    hdr = os.path.join(root, "include", "largesteps_b200.h")
+    for std, lang in (("c99", "c"), ("c++17", "c++")):
+        r = subprocess.run(["gcc", "-std=" + std, "-x", lang, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", hdr],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    out = str(tmp_path / "roundtrip")
+    libdir = os.path.join(root, "large-steps-pytorch_b200", "largesteps_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                        "-I", "/usr/local/cuda/include", os.path.join(root, "examples", "c_host", "roundtrip.c"), "-o", out,
+                        "-L", libdir, "-l:libls_b200.so", "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert os.path.getsize(out) > 0

@@ -43,3 +43,25 @@ def test_integration_md_binding_runs_and_matches_direct_solve():
     torch.cuda.synchronize()
     assert rel_l2(x.cpu().numpy(), oracle.DirectSolver(r, c, val, V).solve(b)) < 1e-5
     del solver
+
+
+def test_pure_c_host_roundtrip(tmp_path):
+    """examples/c_host/roundtrip.c: assembly -> to_differential -> solve -> AdamUniform through the C ABI from a plain C
+    program (no Python, no torch in the process); the program itself checks ||v - verts|| / ||verts|| <= 1e-5."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h"):
+        pytest.skip("gcc or the CUDA headers are not available")
+    out = str(tmp_path / "roundtrip")
+    libdir = os.path.dirname(N.LIB_PATH)
+    cudart_dirs = ["/usr/local/cuda/lib64"]
+    r = subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-I", "/usr/local/cuda/include", os.path.join(ROOT, "examples", "c_host", "roundtrip.c"), "-o", out,
+                        "-L", libdir, "-l:" + os.path.basename(N.LIB_PATH), "-Wl,-rpath," + libdir,
+                        "-L", cudart_dirs[0], "-Wl,-rpath," + cudart_dirs[0], "-lcudart", "-lm"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for n in ("64", "700"):
+        r = subprocess.run([out, n], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "c-abi roundtrip ok" in r.stdout
