@@ -82,6 +82,14 @@ struct PcgHandle {
     int nslices;
     int sell_on;
     int sell_grid;
+    // pattern-only copy for matrices with one common off-diagonal value (ls_sell_kernel.cuh "PAT"; opt-in LS_PCG_PATTERN=1)
+    int *poff;
+    int2 *pcol;
+    float *diagp;
+    unsigned int *patmm;     // [min, max] of the off-diagonal value bits
+    long long pat_cap;       // capacity of `pcol` in pairs
+    float offc;
+    int pat_on;
     // persistent single-kernel solve (K = 3; warm starts enter it in resume mode)
     lsp::GridBar *gbar;
     double *part_persist;
@@ -97,6 +105,11 @@ struct PcgHandle {
     cudaEvent_t ev[2];
     size_t ws_bytes;
 };
+
+static bool want_pattern() {
+    const char *e = getenv("LS_PCG_PATTERN");
+    return e && e[0] == '1';
+}
 
 struct Carve {
     size_t off = 0;
@@ -138,6 +151,13 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
     size_t o_tk = c.take(64);
     size_t o_info = c.take(64);
     size_t o_flags = c.take(64);
+    // pattern-only copy: carved (at the end, so every other offset is the same either way) only when the opt-in is set --
+    // the environment must not change between ls_pcg_workspace_bytes and ls_pcg_create
+    const bool pat = want_pattern();
+    size_t o_poff = c.take(pat ? (size_t)(Vp / 32 + 2) * 4 : 0);
+    size_t o_pcol = c.take(pat ? (size_t)sell_cap * 4 : 0);         // sell_cap / 2 pairs of 8 bytes
+    size_t o_diagp = c.take(pat ? (size_t)Vp * 4 : 0);
+    size_t o_patmm = c.take(pat ? 64 : 0);
     if (h && base) {
         h->Vp = Vp;
         h->rowptr = (int *)(base + o_rp);
@@ -169,6 +189,11 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
         h->tickets = (unsigned int *)(base + o_tk);
         h->info = (float *)(base + o_info);
         h->flags = (int *)(base + o_flags);
+        h->poff = (int *)(base + o_poff);
+        h->pcol = (int2 *)(base + o_pcol);
+        h->diagp = (float *)(base + o_diagp);
+        h->patmm = (unsigned int *)(base + o_patmm);
+        h->pat_cap = sell_cap / 2;
     }
     return c.off;
 }
@@ -711,6 +736,10 @@ int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int max
     a.partials = h->part_persist;
     a.info = info_dev ? info_dev : h->info;
     a.dbg = getenv("LS_PCG_PROFILE") ? h->dbg : nullptr;
+    a.poff = h->poff;
+    a.pcol = h->pcol;
+    a.diagp = h->diagp;
+    a.offc = h->offc;
     LS_CUDA_TRY(cudaMemsetAsync(h->gbar, 0, sizeof(lsp::GridBar), stream));   // barrier counter restarts at 0
     {
         // fast all-reduce slots this solve can touch: 2 per iteration (beyond the ring the kernel uses the slow path)
@@ -728,6 +757,14 @@ int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int max
     else if (a.dbg) {   // profiling build of the same kernel (LS_PCG_PROFILE): per-phase cycle counters in CTA 0
         fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, true, lsp::PWARPS> : (const void *)lsp::pcg_persistent_kernel<3, 0, true, lsp::PWARPS>;
         LS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->persist_smem));
+    }
+    if (h->pat_on) {   // same kernel, pattern-only phase A
+        if (h->persist_threads == lsp::PT_SMALL) fn = (const void *)lsp::pcg_persistent_kernel<3, 1, false, lsp::PT_SMALL / 32, true>;
+        else if (a.dbg) {
+            fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, true, lsp::PWARPS, true> : (const void *)lsp::pcg_persistent_kernel<3, 0, true, lsp::PWARPS, true>;
+            LS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->persist_smem));
+        } else
+            fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, false, lsp::PWARPS, true> : (const void *)lsp::pcg_persistent_kernel<3, 0, false, lsp::PWARPS, true>;
     }
     cudaError_t ce = cudaLaunchCooperativeKernel(fn, dim3(h->persist_grid), dim3(h->persist_threads), params, h->persist_smem, stream);
     if (ce != cudaSuccess) {
@@ -960,6 +997,19 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
     rc = lsk::spmm_plan(h->rowptr, h->part, h->spmm_grid, h->cfg.cap, h->desc, h->desc_cnt, h->flags + 1, stream);
     if (rc) return fail(rc);
 
+    // pattern-only copy (opt-in): are all off-diagonal values bitwise equal?
+    const bool want_pat = want_pattern();
+    unsigned int hmm[2] = {0xffffffffu, 0u};
+    h->pat_on = 0;
+    if (want_pat) {
+        TRY_OR_FAIL(cudaMemsetAsync(h->patmm, 0xff, 4, stream));
+        TRY_OR_FAIL(cudaMemsetAsync(h->patmm + 1, 0, 4, stream));
+        lsk::pat_detect_kernel<<<(unsigned)((V + 255) / 256), 256, 0, stream>>>((int)V, h->rowptr, h->col, h->val, h->patmm);
+        g_ls_launches.fetch_add(1);
+        TRY_OR_FAIL(cudaGetLastError());
+        TRY_OR_FAIL(cudaMemcpyAsync(hmm, h->patmm, sizeof(hmm), cudaMemcpyDeviceToHost, stream));
+    }
+
     int hflags2[2] = {0, 0};
     int sell_total = 0;
     TRY_OR_FAIL(cudaMemcpyAsync(hflags2, h->flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -981,6 +1031,22 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
         if (sg > GRID_CAP) sg = GRID_CAP;
         if (sg < 1) sg = 1;
         h->sell_grid = (int)sg;
+    }
+    if (want_pat && h->sell_on && hmm[0] == hmm[1]) {
+        // every off-diagonal entry carries the same value: build the 4-byte-per-entry copy (no further host round trip:
+        // its padded size is bounded by the general SELL copy's, which fits)
+        memcpy(&h->offc, &hmm[0], 4);
+        const unsigned wb = (unsigned)(((int64_t)h->nslices * 32 + 255) / 256);
+        lsk::pat_width_kernel<<<wb, 256, 0, stream>>>((int)V, h->nslices, h->rowptr, h->col, h->poff);
+        g_ls_launches.fetch_add(1);
+        TRY_OR_FAIL(cudaGetLastError());
+        rc = ls_exclusive_scan_i32(h->poff, h->poff, h->nslices, h->scan, stream);
+        if (rc) return fail(rc);
+        lsk::pat_fill_kernel<<<wb, 256, 0, stream>>>((int)V, h->nslices, h->rowptr, h->col, h->val, h->poff, h->pcol, h->pat_cap,
+                                                      h->offc, h->diagp);
+        g_ls_launches.fetch_add(1);
+        TRY_OR_FAIL(cudaGetLastError());
+        h->pat_on = 1;
     }
     {
         // persistent single-kernel solve: one 768-thread CTA per SM (256 for mid-size meshes), cooperative launch; r / Ap / dinv in shared memory
@@ -1018,6 +1084,20 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
                     h->persist_threads = lsp::PT_SMALL;
                 else
                     cudaGetLastError();
+            }
+            if (ce == cudaSuccess && occ >= 1 && h->pat_on) {
+                // the pattern-only instantiations need the same opt-in shared memory size; if that fails, stay general
+                cudaError_t cp = cudaSuccess;
+                if (h->persist_threads == lsp::PT_SMALL)
+                    cp = cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false, lsp::PT_SMALL / 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                else if (res)
+                    cp = cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false, lsp::PWARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                else
+                    cp = cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 0, false, lsp::PWARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (cp != cudaSuccess) {
+                    cudaGetLastError();
+                    h->pat_on = 0;
+                }
             }
             if (ce == cudaSuccess && occ >= 1) {
                 h->persist_on = 1;
@@ -1157,7 +1237,7 @@ extern "C" int ls_pcg_phase_cycles(void *handle, int64_t *out, int n, void *stre
 extern "C" int ls_pcg_describe(void *handle, int64_t *out8) {
     PcgHandle *h = (PcgHandle *)handle;
     LS_REQUIRE(h != nullptr && out8 != nullptr, "NULL pointer");
-    out8[0] = h->sell_on;                 // 1 = SELL-32 engine, 0 = TMA-staged CSR engine
+    out8[0] = (h->pat_on && h->persist_on) ? 2 : h->sell_on;   // 2 = pattern-only SELL-32 in the persistent kernel, 1 = SELL-32 engine, 0 = TMA-staged CSR engine
     out8[1] = h->sell_entries;            // padded entries of the SELL copy
     out8[2] = h->sell_on ? h->sell_grid : h->spmm_grid;
     out8[3] = h->vec_grid;

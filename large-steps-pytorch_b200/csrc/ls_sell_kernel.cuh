@@ -207,4 +207,71 @@ static __global__ void sell_fill_kernel(int V, int nslices, const int *__restric
     }
 }
 
+// ---- pattern-only SELL-32 ("PAT"): matrices whose off-diagonal entries all carry the same value ---------------------
+// M = I + lambda L with the uniform (combinatorial) Laplacian -- the reference's default, geometry.py:112-133 -- has
+// M_ij = -lambda for every edge: only the diagonal differs from row to row.  For such matrices the solver streams column
+// indices alone, 4 bytes per entry instead of 8, and leaves the diagonal out of the gather list (the owner loads its own
+// p row anyway):   (M p)_i = d'_i p_i + c * sum_{j in slots(i)} p_j .
+// Layout: slice s holds 32 * w2 int2 "pairs" at pc[poff[s] ...], pair (m, lane) = slots 2m and 2m+1 of row 32 s + lane, one
+// 8-byte load per lane per pair.  Unused slots point at the row itself and are paid back in the diagonal:
+// d'_i = M_ii - c * (unused slots of row i), so the inner loop has no per-lane predicate.
+// Opt-in for now (LS_PCG_PATTERN=1); detection is exact (bitwise equality of all off-diagonal values).
+static __global__ void pat_detect_kernel(int V, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                         const float *__restrict__ val, unsigned int *__restrict__ mm /* [min, max] */) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int mn = 0xffffffffu, mx = 0u;
+    if (row < V) {
+        for (int j = rowptr[row]; j < rowptr[row + 1]; ++j)
+            if (col[j] != row) {
+                const unsigned int b = __float_as_uint(val[j]);
+                mn = min(mn, b);
+                mx = max(mx, b);
+            }
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) {
+        if (mn != 0xffffffffu) atomicMin(mm, mn);
+        if (mx != 0u) atomicMax(mm + 1, mx);
+    }
+}
+// widths: one warp per slice, cnt[s] = 32 * ceil(max off-diagonal row length / 2)   (in pairs)
+static __global__ void pat_width_kernel(int V, int nslices, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                        int *__restrict__ cnt) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= nslices) return;
+    const int row = gw * 32 + lane;
+    int len = 0;
+    if (row < V)
+        for (int j = rowptr[row]; j < rowptr[row + 1]; ++j) len += (col[j] != row) ? 1 : 0;
+    len = __reduce_max_sync(0xffffffffu, len);
+    if (lane == 0) cnt[gw] = 32 * ((len + 1) >> 1);
+}
+static __global__ void pat_fill_kernel(int V, int nslices, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                       const float *__restrict__ val, const int *__restrict__ poff, int2 *__restrict__ pc,
+                                       long long cap_pairs, float offc, float *__restrict__ diagp) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= nslices) return;
+    const int o0 = poff[gw], o1 = poff[gw + 1];
+    if ((long long)o1 > cap_pairs) return;
+    const int w2 = (o1 - o0) >> 5;
+    const int row = gw * 32 + lane;
+    int *slots = reinterpret_cast<int *>(pc);
+    float d = 0.f;
+    int j = 0;
+    if (row < V)
+        for (int e = rowptr[row]; e < rowptr[row + 1]; ++e) {
+            const int c = col[e];
+            if (c == row) {
+                d = val[e];
+            } else {
+                slots[2 * ((size_t)o0 + (size_t)(j >> 1) * 32 + lane) + (j & 1)] = c;
+                ++j;
+            }
+        }
+    const int used = j;
+    for (; j < 2 * w2; ++j) slots[2 * ((size_t)o0 + (size_t)(j >> 1) * 32 + lane) + (j & 1)] = row;   // unused slot: the row itself
+    diagp[row] = (row < V) ? fmaf(-offc, (float)(2 * w2 - used), d) : 0.f;
+}
+
 }  // namespace lsk

@@ -1,0 +1,63 @@
+"""GPU, EXPERIMENTAL (opt-in LS_PCG_PATTERN=1): pattern-only matrix copy in the persistent solver (4 bytes per entry for
+matrices whose off-diagonal values are all equal -- the uniform Laplacian; csrc/ls_sell_kernel.cuh "PAT").
+
+The code was written after round 1's GPU budget was spent: its algebra is checked on the CPU (tests/test_host_logic.py::
+test_pattern_layout_model) and the default path's SASS was verified unchanged, but it has not run on hardware yet.  So:
+  * it runs in a SUBPROCESS with a timeout (a fault in it cannot poison this process's CUDA context or hang the suite),
+  * it is xfail(strict=False): XPASS means the path works on this box; a failure here says nothing about the default path.
+The file sorts last on purpose."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+CASE = r'''
+import os, sys
+sys.path.insert(0, os.path.join(ROOT, "large-steps-pytorch_b200")); sys.path.insert(0, ROOT)
+import numpy as np, torch, oracle
+from largesteps_b200 import workloads
+from largesteps_b200.geometry import compute_matrix
+from largesteps_b200.parameterize import to_differential
+from largesteps_b200.solvers import PCGSolver
+d = np.load(os.path.join(ROOT, "tests", "golden", "bunny_mesh.npz"))
+bv, bf = workloads.subdivide(d["verts"], d["faces"].astype(np.int64))
+n = 21                                                     # fan: one vertex of valence 21 (wide-slice loop)
+ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+fanv = np.vstack([[0, 0, 0.5], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)]).astype(np.float32)
+fanf = np.array([[0, 1 + i, 1 + (i + 1) % n] for i in range(n)])
+cases = [("fan21", fanv, fanf, dict(lambda_=3.0)),
+         ("plane64", *workloads.plane(64, seed=0), dict(lambda_=19.0)),            # single CTA
+         ("plane300", *workloads.plane(300, seed=0), dict(lambda_=19.0)),          # 148 CTAs, 768 threads
+         ("bunny_x1", bv.astype(np.float32), bf, dict(lambda_=1.0, alpha=0.9)),    # irregular valence, 256-thread CTAs
+         ("plane300_cot", *workloads.plane(300, seed=0), dict(lambda_=19.0, cotan=True))]   # not uniform: must stay general
+for name, v, f, kw in cases:
+    tv, tf = torch.from_numpy(np.asarray(v, np.float32)).cuda(), torch.from_numpy(np.asarray(f)).cuda()
+    M = compute_matrix(tv, tf, **kw)
+    s = PCGSolver(M, check=True)
+    eng = s.describe()["sell_engine"]
+    assert eng == (1 if kw.get("cotan") else 2), (name, eng)
+    u = to_differential(M, tv)
+    x = s.solve(u)
+    torch.cuda.synchronize()
+    r, c, val, V = oracle.compute_matrix(np.asarray(v, np.float64), np.asarray(f), **kw)
+    xd = oracle.DirectSolver(r, c, val, V).solve(u.cpu().numpy())
+    err = np.linalg.norm(x.cpu().numpy() - xd) / np.linalg.norm(xd)
+    assert err < 1e-5, (name, err)
+    x2 = s.solve(u); torch.cuda.synchronize()
+    assert torch.equal(x, x2), name                      # deterministic
+    print(name, "engine", eng, "iterations", s.iterations, "err %.2e" % err)
+print("pattern path ok")
+'''
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in path not yet validated on hardware (written after the round's GPU budget was spent)")
+def test_pattern_only_copy_solves_to_parity():
+    env = dict(os.environ, LS_PCG_PATTERN="1")
+    r = subprocess.run([sys.executable, "-c", f"ROOT = r'{ROOT}'\n" + CASE], env=env, capture_output=True, text=True, timeout=300)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "pattern path ok" in r.stdout

@@ -158,3 +158,71 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "icosphere",
                           "--steps", "1"], capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_pattern_layout_model(bunny_mesh):
+    """CPU model of the opt-in pattern-only matrix copy (csrc/ls_sell_kernel.cuh pat_fill_kernel + the PAT phase A of
+    ls_pcg_persistent.cuh): slots, self-pointing padding and the diagonal pay-back reproduce M @ p to fp32 rounding,
+    including slices wider than the 4 register pairs (bunny: valence up to 10+) and narrower than 3."""
+    import numpy as np
+    import scipy.sparse as sp
+    import oracle
+    f32 = np.float32
+    U = 4
+
+    def run(v, f, lam):
+        rows, cols, vals, V = oracle.compute_matrix(np.asarray(v, np.float64), np.asarray(f), lambda_=lam)
+        A = sp.csr_matrix((vals.astype(f32), (rows, cols)), shape=(V, V))
+        A.sort_indices()
+        rp, ci, va = A.indptr, A.indices, A.data
+        off = va[ci != np.repeat(np.arange(V), np.diff(rp))]
+        assert off.min() == off.max()            # what pat_detect_kernel establishes (bitwise)
+        c = f32(off[0])
+        Vp = (V + 31) // 32 * 32
+        p = np.zeros((Vp, 3), f32)
+        p[:V] = np.random.default_rng(0).normal(size=(V, 3)).astype(f32)
+        y = np.zeros((Vp, 3), f32)
+        widths = set()
+        for s in range(Vp // 32):
+            rws = range(32 * s, 32 * s + 32)
+            w2 = (max(int(np.sum(ci[rp[r]:rp[r + 1]] != r)) if r < V else 0 for r in rws) + 1) // 2
+            widths.add(w2)
+            for r in rws:
+                slots, d = [], f32(0)
+                if r < V:
+                    for e in range(rp[r], rp[r + 1]):
+                        if ci[e] == r:
+                            d = va[e]
+                        else:
+                            slots.append(int(ci[e]))
+                used = len(slots)
+                slots += [r] * (2 * w2 - used)                       # unused stored slots point at the row itself ...
+                dp = f32(d - c * f32(2 * w2 - used)) if r < V else f32(0)   # ... and are paid back in the diagonal
+                pairs = [(slots[2 * m], slots[2 * m + 1]) for m in range(w2)]
+                UB = 3 if w2 <= 3 else 4
+                chunk = pairs[:UB] + [(r, r)] * (UB - min(w2, UB))   # register slots past the width: same trick
+                dp = f32(dp - c * f32(2 * (UB - min(w2, UB))))
+                sm = np.zeros(3, f32)
+                for a, b in chunk:
+                    sm = (sm + (p[a] + p[b]).astype(f32)).astype(f32)
+                j = U
+                while j < w2:
+                    for a, b in pairs[j:j + U] + [(r, r)] * max(0, j + U - w2):
+                        sm = (sm + (p[a] + p[b]).astype(f32)).astype(f32)
+                    dp = f32(dp - c * f32(2 * max(0, j + U - w2)))
+                    j += U
+                y[r] = (dp * p[r] + c * sm).astype(f32)
+        ref = A.astype(np.float64) @ p[:V].astype(np.float64)
+        return np.linalg.norm(y[:V] - ref) / np.linalg.norm(ref), widths
+
+    from largesteps_b200 import workloads
+    err, widths = run(*bunny_mesh, 19.0)
+    assert err < 5e-7 and max(widths) == 4
+    n = 21                                            # a fan: one vertex of valence 21 -> 11 pairs, three passes of the wide-slice loop
+    ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    fv = np.vstack([[0, 0, 0], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)])
+    ff = np.array([[0, 1 + i, 1 + (i + 1) % n] for i in range(n)])
+    err, widths = run(fv, ff, 3.0)
+    assert err < 5e-7 and max(widths) > 2 * U
+    err, widths = run(*workloads.plane(12), 5.0)
+    assert err < 5e-7 and min(widths) <= 3           # exercises the 3-pair body and its pay-back
