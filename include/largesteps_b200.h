@@ -95,6 +95,7 @@ int ls_spmm_csr_f32(int64_t V, const int32_t *rowptr, const int32_t *col, const 
  *       numbering), extracts the Jacobi diagonal, balances the row partition, plans the SpMM blocks.
  *       The caller keeps `workspace` alive until ls_pcg_destroy.  Synchronises `stream`.
  *       precond: 0 = none, 1 = Jacobi.   k_max in [1,4].
+ *       The workspace size depends on (V, nnz, k_max) only -- never on the environment.
  *   ls_pcg_solve:  b, x: (V,k) float32 row-major contiguous (ld = k); x0 = NULL for a cold start (x0 may alias x).
  *       rtol: stop when ||r_j||_2 <= rtol * ||b_j||_2 for every column j (columns freeze independently, which
  *       is what the reference's per-axis solves do, solvers.py:115-118).  maxit > 0.
@@ -109,19 +110,18 @@ int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz,
 int ls_pcg_solve(void *handle, const float *b, float *x, const float *x0, int k,
                  float rtol, int maxit, float *info_dev, float *info_host, void *stream);
 int ls_pcg_destroy(void *handle);
-/* in-solver SpMM of the handle's own matrix copy on SoA planes, for profiling the dominant kernel:
- *   runs `launches` back-to-back launches of the solver's SpMM+dot kernel on its internal p/Ap planes.  */
-int ls_pcg_bench_spmm(void *handle, int k, int launches, void *stream);
-/* timing harness for the iteration kernels, launched back-to-back from C (a Python-level loop is launch-bound):
- *   `launches` launches rotating over `n_handles` handles (use enough handles that matrix+vectors exceed L2 for an
- *   HBM-cold number, one handle for the L2-resident number).  which: 0 SpMM+dot, 1 update, 2 p-update, 3 all three. */
-int ls_pcg_bench(void **handles, int n_handles, int k, int which, int launches, void *stream);
-/* with LS_PCG_PROFILE set in the environment the persistent kernel's CTA 0 accumulates SM-clock cycles per phase of
- * the last solve: out8 = [SpMM phase, all-reduce 1, update phase, all-reduce 2, p-update phase, barrier 3, 0, iterations] */
-int ls_pcg_phase_cycles(void *handle, int64_t *out, int n /* 8, or 8 + 8*grid for the per-CTA table (.., smid, it) */, void *stream);
-/* introspection: out8 = [engine (1 SELL-32, 0 TMA-staged CSR), padded SELL entries, SpMM grid, vector-kernel grid,
- *                        solve mode (0 graph of 3 kernels / 1 persistent, r+Ap global / 2 persistent, r+Ap in smem),
- *                        persistent grid, block plan valid, re-ordered]                                             */
+/* Accuracy guard of the fused solver (csrc/ls_pcg_fused.cuh).  When the iteration has converged on its recursive residual
+ * the kernel evaluates the TRUE residual b - M x with fp64 accumulation; if, for some column, it exceeds both rtol ||b|| and
+ * theta * 2^-24 * || |M| |x| || (theta times the floor that storing x in fp32 imposes), the iteration restarts from that
+ * residual, at most max_restarts times per solve.  Defaults: max_restarts = 1, theta = 3.  max_restarts = 0 switches the
+ * check off.  (The reference's direct solve has no such knob: solvers.py:36-39.)                                            */
+int ls_pcg_set_refinement(void *handle, int max_restarts, float theta);
+/* introspection.  Fused solver (default): out8 = [matrix copy (2 pattern-only SELL-32 / 1 general SELL-32), padded SELL
+ *   entries, CTAs, cluster size (0 = cooperative grid), 10 + residency level (0 vectors in global memory, 1 r/s/D^-1 in
+ *   shared memory, 2 also x and p), CTAs, threads per CTA, re-ordered].
+ *   Older paths (LS_PCG_ALGO=classic / LS_PCG_MODE=graph): out8 = [engine (2, 1, 0 = TMA-staged CSR), padded SELL entries,
+ *   SpMM grid, vector-kernel grid, mode (0 graph of 3 kernels / 1 persistent, r+Ap global / 2 persistent, r+Ap in smem),
+ *   persistent grid, block plan valid, re-ordered]                                                                   */
 int ls_pcg_describe(void *handle, int64_t *out8);
 /* algorithmic bytes of one in-solver SpMM launch: 8 nnz + 4 (V+1) + 8 k V  (SURVEY.md section 8 d)      */
 int64_t ls_pcg_spmm_bytes(void *handle, int k);

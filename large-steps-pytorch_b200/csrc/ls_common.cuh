@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <atomic>
 #include "../../include/largesteps_b200.h"
+#include "../../include/largesteps_b200_diag.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "libls_b200 is written for sm_100a (Blackwell B200) only"

@@ -29,6 +29,7 @@
 #include "ls_spmm_host.h"
 #include "ls_sell_kernel.cuh"
 #include "ls_pcg_persistent.cuh"
+#include "ls_pcg_fused.cuh"
 
 namespace {
 
@@ -98,6 +99,17 @@ struct PcgHandle {
     int ring_slots;
     int persist_on, persist_grid, persist_res, persist_nsl_max, persist_threads;
     size_t persist_smem;
+    // fused two-synchronisation solver (ls_pcg_fused.cuh): the default; one configuration for K = 3 (k = 1..3) and one for K = 4
+    float *pv;               // owner copy of p, k_max planes
+    struct FusedCfg {
+        int on, grid, res, nw, sync, cluster, nsl_max, pat;
+        size_t smem;
+        const void *fn, *fn_prof;
+    } fused[2];
+    int max_smem_optin;
+    int refine;              // max restarts from the true residual per solve
+    float theta;
+    int sell_tma;            // stand-alone SpMM: TMA-staged variant (0 = register-prefetch kernel)
     // graphs, one per K
     cudaGraphExec_t graph[KMAX + 1];
     cudaStream_t cap_stream;
@@ -106,9 +118,9 @@ struct PcgHandle {
     size_t ws_bytes;
 };
 
-static bool want_pattern() {
+static bool want_pattern() {   // on unless LS_PCG_PATTERN=0 (A/B switch)
     const char *e = getenv("LS_PCG_PATTERN");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
 }
 
 struct Carve {
@@ -131,6 +143,7 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
     size_t o_r = c.take((size_t)Vp * 4 * k_max);
     size_t o_p = c.take((size_t)Vp * 4 * 4);            // p: rows of PW <= 4 floats
     size_t o_Ap = c.take((size_t)Vp * 4 * k_max);
+    size_t o_pown = c.take((size_t)Vp * 4 * k_max);
     size_t o_part = c.take((size_t)(grid_cap + 1) * 4);
     size_t o_desc = c.take((size_t)grid_cap * lsk::SPMM_BMAX * sizeof(int4));
     size_t o_dcnt = c.take((size_t)grid_cap * 4);
@@ -144,20 +157,18 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
     size_t o_ps = c.take((size_t)grid_cap * KMAX * 8);
     size_t o_pv = c.take((size_t)grid_cap * 3 * KMAX * 8);
     size_t o_gbar = c.take(64);
-    size_t o_pp = c.take((size_t)2 * lsp::NVMAX * 256 * 8);
+    size_t o_pp = c.take((size_t)2 * lsf::NVMAX * 256 * 8);
     size_t o_dbg = c.take((size_t)(8 + 8 * 256) * 8);
     constexpr int RING_SLOTS = 32768;                 // fast all-reduce slots (64 B each): 2 per iteration
     size_t o_ring = c.take((size_t)RING_SLOTS * 64);
     size_t o_tk = c.take(64);
     size_t o_info = c.take(64);
     size_t o_flags = c.take(64);
-    // pattern-only copy: carved (at the end, so every other offset is the same either way) only when the opt-in is set --
-    // the environment must not change between ls_pcg_workspace_bytes and ls_pcg_create
-    const bool pat = want_pattern();
-    size_t o_poff = c.take(pat ? (size_t)(Vp / 32 + 2) * 4 : 0);
-    size_t o_pcol = c.take(pat ? (size_t)sell_cap * 4 : 0);         // sell_cap / 2 pairs of 8 bytes
-    size_t o_diagp = c.take(pat ? (size_t)Vp * 4 : 0);
-    size_t o_patmm = c.take(pat ? 64 : 0);
+    // pattern-only copy (always carved: the workspace size must not depend on the environment)
+    size_t o_poff = c.take((size_t)(Vp / 32 + 2) * 4);
+    size_t o_pcol = c.take((size_t)sell_cap * 4);         // sell_cap / 2 pairs of 8 bytes
+    size_t o_diagp = c.take((size_t)Vp * 4);
+    size_t o_patmm = c.take(64);
     if (h && base) {
         h->Vp = Vp;
         h->rowptr = (int *)(base + o_rp);
@@ -168,6 +179,7 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
         h->r = (float *)(base + o_r);
         h->p = (float *)(base + o_p);
         h->Ap = (float *)(base + o_Ap);
+        h->pv = (float *)(base + o_pown);
         h->part = (int *)(base + o_part);
         h->desc = (int4 *)(base + o_desc);
         h->desc_cnt = (int *)(base + o_dcnt);
@@ -636,6 +648,44 @@ lsk::SpmmArgs spmm_args(PcgHandle *h, int K, bool with_done) {
     return s;
 }
 
+// TMA-staged SELL SpMM (ls_sell_kernel.cuh): per-warp shared-memory rings fed by cp.async.bulk, launched with programmatic
+// stream serialisation so that its matrix prefetch overlaps the tail of the previous kernel in the stream.
+template <int K, int NW, int DEPTH>
+int launch_sell_tma_t(PcgHandle *h, const lsk::SellArgs &a, cudaStream_t s) {
+    static bool prepared = false;
+    const size_t smem = lsk::sell_tma_smem_bytes(NW, DEPTH);
+    if (!prepared) {
+        LS_CUDA_TRY(cudaFuncSetAttribute(lsk::spmm_sell_tma_kernel<K, true, NW, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prepared = true;
+    }
+    cudaLaunchConfig_t lc = {};
+    int g = h->nslices < h->sm_count ? h->nslices : h->sm_count;
+    lc.gridDim = dim3(g < 1 ? 1 : g);
+    lc.blockDim = dim3(NW * 32);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = (h->sell_tma >= 10) ? 0 : 1;   // LS_SELL_TMA >= 10: same kernels without PDL (A/B)
+    LS_CUDA_TRY(cudaLaunchKernelEx(&lc, lsk::spmm_sell_tma_kernel<K, true, NW, DEPTH>, a));
+    g_ls_launches.fetch_add(1, std::memory_order_relaxed);
+    return LS_OK;
+}
+template <int K>
+int launch_sell_tma(PcgHandle *h, const lsk::SellArgs &a, cudaStream_t s) {
+    if constexpr (K == 3) {
+        switch (h->sell_tma % 10) {
+            case 2: return launch_sell_tma_t<K, 24, 4>(h, a, s);
+            case 3: return launch_sell_tma_t<K, 32, 2>(h, a, s);
+            case 4: return launch_sell_tma_t<K, 16, 6>(h, a, s);
+            default: break;
+        }
+    }
+    return launch_sell_tma_t<K, 32, 3>(h, a, s);
+}
+
 template <int K>
 int launch_spmm(PcgHandle *h, bool with_done, cudaStream_t s) {
     if (h->sell_on) {
@@ -651,6 +701,7 @@ int launch_spmm(PcgHandle *h, bool with_done, cudaStream_t s) {
         a.partials = h->part_spmm;
         a.ticket = h->tickets + 0;
         a.dot_out = h->ctrl->pAp;
+        if (h->sell_tma) return launch_sell_tma<K>(h, a, s);
         lsk::spmm_sell_kernel<K, true><<<h->sell_grid, lsk::SELL_THREADS, 0, s>>>(a);
         LS_LAUNCH_CHECK();
         return LS_OK;
@@ -691,7 +742,7 @@ int build_graph(PcgHandle *h) {
 
 int finish_info(PcgHandle *h, float rtol, int maxit, float *info_src, float *info_host, cudaStream_t stream) {
     if (!info_host) return LS_OK;
-    LS_CUDA_TRY(cudaMemcpyAsync(info_host, info_src, 8 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    LS_CUDA_TRY(cudaMemcpyAsync(info_host, info_src, 8 * sizeof(float), cudaMemcpyDefault, stream));
     LS_CUDA_TRY(cudaStreamSynchronize(stream));
     const int st = (int)info_host[1];
     if (st == 3) {
@@ -756,13 +807,13 @@ int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int max
     if (h->persist_threads == lsp::PT_SMALL) fn = (const void *)lsp::pcg_persistent_kernel<3, 1, false, lsp::PT_SMALL / 32>;
     else if (a.dbg) {   // profiling build of the same kernel (LS_PCG_PROFILE): per-phase cycle counters in CTA 0
         fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, true, lsp::PWARPS> : (const void *)lsp::pcg_persistent_kernel<3, 0, true, lsp::PWARPS>;
-        LS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->persist_smem));
+        LS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
     }
     if (h->pat_on) {   // same kernel, pattern-only phase A
         if (h->persist_threads == lsp::PT_SMALL) fn = (const void *)lsp::pcg_persistent_kernel<3, 1, false, lsp::PT_SMALL / 32, true>;
         else if (a.dbg) {
             fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, true, lsp::PWARPS, true> : (const void *)lsp::pcg_persistent_kernel<3, 0, true, lsp::PWARPS, true>;
-            LS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->persist_smem));
+            LS_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
         } else
             fn = h->persist_res ? (const void *)lsp::pcg_persistent_kernel<3, 1, false, lsp::PWARPS, true> : (const void *)lsp::pcg_persistent_kernel<3, 0, false, lsp::PWARPS, true>;
     }
@@ -779,9 +830,221 @@ int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int max
     return finish_info(h, rtol, maxit, a.info, info_host, stream);
 }
 
+// ---- fused two-synchronisation solver (ls_pcg_fused.cuh) ------------------------------------------------------------
+// instantiation table: (K, RES, NW, PAT, SYNC, PROF) -> kernel, or NULL when that combination is not built
+template <int K, int RES, int NW, bool PAT, int SYNC, bool PROF>
+const void *ffn() { return (const void *)lsf::pcg_fused_kernel<K, RES, NW, PAT, SYNC, PROF>; }
+
+const void *fused_fn(int K, int res, int nw, int pat, int sync, int prof) {
+    constexpr int W = lsp::PWARPS, WS = lsp::PT_SMALL / 32;
+    if (K == 3 && !prof) {
+        if (sync == 0 && nw == W) {
+            if (res == 0) return pat ? ffn<3, 0, W, true, 0, false>() : ffn<3, 0, W, false, 0, false>();
+            if (res == 1) return pat ? ffn<3, 1, W, true, 0, false>() : ffn<3, 1, W, false, 0, false>();
+            if (res == 2) return pat ? ffn<3, 2, W, true, 0, false>() : ffn<3, 2, W, false, 0, false>();
+        }
+        if (sync == 0 && nw == WS && res == 2) return pat ? ffn<3, 2, WS, true, 0, false>() : ffn<3, 2, WS, false, 0, false>();
+        if (sync == 1 && nw == W && res == 2) return pat ? ffn<3, 2, W, true, 1, false>() : ffn<3, 2, W, false, 1, false>();
+    }
+    if (K == 3 && prof && nw == W) {
+        if (sync == 0 && res == 1) return pat ? ffn<3, 1, W, true, 0, true>() : ffn<3, 1, W, false, 0, true>();
+        if (sync == 0 && res == 2) return pat ? ffn<3, 2, W, true, 0, true>() : ffn<3, 2, W, false, 0, true>();
+        if (sync == 1 && res == 2) return pat ? ffn<3, 2, W, true, 1, true>() : ffn<3, 2, W, false, 1, true>();
+    }
+    if (K == 4 && !prof && !pat && nw == W) {
+        if (sync == 0 && res == 0) return ffn<4, 0, W, false, 0, false>();
+        if (sync == 0 && res == 1) return ffn<4, 1, W, false, 0, false>();
+        if (sync == 0 && res == 2) return ffn<4, 2, W, false, 0, false>();
+        if (sync == 1 && res == 2) return ffn<4, 2, W, false, 1, false>();
+    }
+    return nullptr;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+
+// Choose grid / cluster, residency and CTA shape for one K.  Small meshes (the CTA-resident rows of <= 16 SMs hold them)
+// run as ONE thread-block cluster; everything else as a cooperative grid with one CTA per SM.
+int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCfg *c) {
+    memset(c, 0, sizeof(*c));
+    if (!h->sell_on) return LS_OK;
+    const char *algo = getenv("LS_PCG_ALGO");
+    if (algo && (algo[0] == 'c' || algo[0] == 'C')) return LS_OK;          // A/B: round-1 three-synchronisation kernel
+    const char *mode = getenv("LS_PCG_MODE");
+    if (mode && (mode[0] == 'g' || mode[0] == 'G')) return LS_OK;
+    const int pat = (K == 3 && h->pat_on) ? 1 : 0;
+    const int W = lsp::PWARPS;
+    auto cap_slices = [&](int res) {   // slices per CTA that fit in shared memory at this residency level
+        if (res == 0) return 1 << 30;
+        int n = 0;
+        while (lsf::fused_smem_bytes(K, res, n + 1) <= (size_t)di.max_smem_optin) ++n;
+        return n;
+    };
+    const int cap2 = cap_slices(2), cap1 = cap_slices(1);
+    const int want_cluster = env_int("LS_PCG_CLUSTER", -1);   // -1 auto, 0 never, N force cluster size N
+    const int force_res = env_int("LS_PCG_RES", -1);
+    // ---- one cluster?
+    int cs = 0;
+    if (want_cluster != 0) {
+        if (h->nslices <= 4 * W) cs = 1;
+        else if ((h->nslices + 15) / 16 <= cap2) cs = 16;
+        if (want_cluster > 0) cs = want_cluster;
+        if (cs > 0 && (h->nslices + cs - 1) / cs > cap2) cs = 0;
+    }
+    if (cs > 0) {
+        const void *fn = fused_fn(K, 2, W, pat, 1, 0);
+        const int nsl_max = (h->nslices + cs - 1) / cs;
+        const size_t smem = lsf::fused_smem_bytes(K, 2, nsl_max);
+        bool ok = fn != nullptr;
+        if (ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin) != cudaSuccess) ok = false;
+        if (ok && cs > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = false;
+        if (ok && cs > 1) {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(cs);
+            lc.blockDim = dim3(W * 32);
+            lc.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            lc.attrs = at;
+            lc.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, fn, &lc) != cudaSuccess || ncl < 1) ok = false;
+        }
+        if (ok) {
+            c->on = 1; c->grid = cs; c->res = 2; c->nw = W; c->sync = 1; c->cluster = cs; c->nsl_max = nsl_max; c->pat = pat;
+            c->smem = smem; c->fn = fn; c->fn_prof = fused_fn(K, 2, W, pat, 1, 1);
+            if (c->fn_prof) {
+                cudaFuncSetAttribute(c->fn_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
+                if (cs > 8) cudaFuncSetAttribute(c->fn_prof, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            }
+            cudaGetLastError();
+            return LS_OK;
+        }
+        cudaGetLastError();
+    }
+    // ---- cooperative grid, one CTA per SM
+    int coop = 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, di.device) != cudaSuccess || !coop) {
+        cudaGetLastError();
+        return LS_OK;
+    }
+    int g = di.sm_count < h->nslices ? di.sm_count : h->nslices;
+    if (g > 255) g = 255;
+    if (g < 1) g = 1;
+    const int nsl_max = (h->nslices + g - 1) / g;
+    int res = nsl_max <= cap2 ? 2 : (nsl_max <= cap1 ? 1 : 0);
+    if (force_res >= 0 && force_res < res) res = force_res;
+    int nw = W;
+    const char *et = getenv("LS_PCG_SMALLCTA");
+    if (K == 3 && res == 2 && nsl_max <= 16 && !(et && et[0] == '0')) nw = lsp::PT_SMALL / 32;
+    const void *fn = fused_fn(K, res, nw, pat, 0, 0);
+    if (!fn) return LS_OK;
+    const size_t smem = lsf::fused_smem_bytes(K, res, nsl_max);
+    // the attribute is per function and device, shared by every handle: always the device maximum, never a per-handle size
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin) != cudaSuccess) {
+        cudaGetLastError();
+        return LS_OK;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, nw * 32, smem) != cudaSuccess || occ < 1 || occ * di.sm_count < g) {
+        cudaGetLastError();
+        return LS_OK;
+    }
+    c->on = 1; c->grid = g; c->res = res; c->nw = nw; c->sync = 0; c->cluster = 0; c->nsl_max = nsl_max; c->pat = pat;
+    c->smem = smem; c->fn = fn; c->fn_prof = fused_fn(K, res, nw, pat, 0, 1);
+    if (c->fn_prof) cudaFuncSetAttribute(c->fn_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
+    cudaGetLastError();
+    return LS_OK;
+}
+
+int solve_fused(PcgHandle *h, const float *b, float *x, const float *x0, int k, float rtol, int maxit, float *info_dev,
+                float *info_host, cudaStream_t stream) {
+    PcgHandle::FusedCfg &c = h->fused[k == 4 ? 1 : 0];
+    lsf::FusedArgs a{};
+    a.V = (int)h->V;
+    a.Vp = h->Vp;
+    a.nslices = h->nslices;
+    a.nsl_max = c.nsl_max;
+    a.kb = k;
+    a.soff = h->soff;
+    a.ent = h->ent;
+    a.poff = h->poff;
+    a.pcol = h->pcol;
+    a.diagp = h->diagp;
+    a.offc = h->offc;
+    a.dinv = h->dinv;
+    a.x = h->x;
+    a.pv = h->pv;
+    a.r = h->r;
+    a.s = h->Ap;
+    a.z = h->p;
+    a.b = b;
+    a.out = x;
+    a.x0 = x0;
+    a.perm = h->has_perm ? h->perm : nullptr;
+    a.rtol = rtol;
+    a.maxit = maxit;
+    a.refine = h->refine;
+    a.theta = h->theta;
+    a.bar = h->gbar;
+    a.partials = h->part_persist;
+    a.info = info_dev ? info_dev : h->info;
+    const bool prof = getenv("LS_PCG_PROFILE") != nullptr && c.fn_prof != nullptr;
+    a.dbg = prof ? h->dbg : nullptr;
+    const void *fn = prof ? c.fn_prof : c.fn;
+    void *params[] = {(void *)&a};
+    cudaError_t ce;
+    if (c.sync == 1) {
+        if (c.cluster > 1) {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(c.grid);
+            lc.blockDim = dim3(c.nw * 32);
+            lc.dynamicSmemBytes = c.smem;
+            lc.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = c.cluster;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            lc.attrs = at;
+            lc.numAttrs = 1;
+            ce = cudaLaunchKernelExC(&lc, fn, params);
+        } else {
+            ce = cudaLaunchKernel(fn, dim3(1), dim3(c.nw * 32), params, c.smem, stream);
+        }
+    } else {
+        LS_CUDA_TRY(cudaMemsetAsync(h->gbar, 0, sizeof(lsp::GridBar), stream));
+        long long need = 2LL * maxit + 64;
+        if (need > h->ring_slots) need = h->ring_slots;
+        const char *e = getenv("LS_PCG_FASTRED");
+        a.ring = h->ring;
+        a.ring_slots = (e && e[0] == '0') ? 0 : (int)need;
+        if (e && atoi(e) > 0 && atoi(e) < a.ring_slots) a.ring_slots = atoi(e);
+        if (a.ring_slots > 0) LS_CUDA_TRY(cudaMemsetAsync(h->ring, 0, (size_t)a.ring_slots * 64, stream));
+        ce = cudaLaunchCooperativeKernel(fn, dim3(c.grid), dim3(c.nw * 32), params, c.smem, stream);
+    }
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        c.on = 0;   // e.g. a partitioned device that cannot co-schedule the grid: the older paths compute the same thing
+        ls_set_error("launch of the fused solver failed (%s); falling back", cudaGetErrorString(ce));
+        return -1;
+    }
+    g_ls_launches.fetch_add(1, std::memory_order_relaxed);
+    return finish_info(h, rtol, maxit, a.info, info_host, stream);
+}
+
 template <int K>
 int solve_k(PcgHandle *h, const float *b, float *x, const float *x0, float rtol, int maxit, float *info_dev,
             float *info_host, cudaStream_t stream) {
+    if (h->fused[K == 4 ? 1 : 0].on) {
+        const int frc = solve_fused(h, b, x, x0, K, rtol, maxit, info_dev, info_host, stream);
+        if (frc != -1) return frc;
+    }
     if (K == 3 && h->persist_on && x0 == nullptr) {
         const int prc = solve_persistent(h, b, x, rtol, maxit, info_dev, info_host, stream, false);
         if (prc != -1) return prc;     // -1: cooperative launch refused, fall through to the graph-mode solver
@@ -832,7 +1095,7 @@ int solve_k(PcgHandle *h, const float *b, float *x, const float *x0, float rtol,
     k_final<K><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va, x, info_dev ? info_dev : h->info);
     LS_LAUNCH_CHECK();
     if (info_host) {
-        LS_CUDA_TRY(cudaMemcpyAsync(info_host, info_dev ? info_dev : h->info, 8 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        LS_CUDA_TRY(cudaMemcpyAsync(info_host, info_dev ? info_dev : h->info, 8 * sizeof(float), cudaMemcpyDefault, stream));
         LS_CUDA_TRY(cudaStreamSynchronize(stream));
         const int st = (int)info_host[1];
         if (st == 3) {
@@ -886,6 +1149,10 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
     h->precond = precond;
     h->device = di.device;
     h->sm_count = di.sm_count;
+    h->max_smem_optin = di.max_smem_optin;
+    h->refine = env_int("LS_PCG_REFINE", 1);
+    h->sell_tma = env_int("LS_SELL_TMA", 1);
+    h->theta = 3.0f;
     h->ws_bytes = need;
     carve_handle(h, (char *)workspace, V, nnz, k_max, GRID_CAP);
 
@@ -1069,8 +1336,8 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
                 res = 0;
                 smem = lsp::persist_smem_bytes(3, 0, nsl_max);
             }
-            cudaError_t ce = res ? cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false, lsp::PWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                 : cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 0, false, lsp::PWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t ce = res ? cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false, lsp::PWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin)
+                                 : cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 0, false, lsp::PWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
             int occ = 0;
             if (ce == cudaSuccess)
                 ce = res ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lsp::pcg_persistent_kernel<3, 1, false, lsp::PWARPS>, lsp::PT, smem)
@@ -1080,7 +1347,7 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
             if (ce == cudaSuccess && occ >= 1 && res == 1 && g > 1 && nsl_max <= 16 && !(et && et[0] == '0')) {
                 // a CTA owns only a handful of slices: 8 warps are enough and make every CTA-level barrier cheaper
                 if (cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false, lsp::PT_SMALL / 32>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin) == cudaSuccess)
                     h->persist_threads = lsp::PT_SMALL;
                 else
                     cudaGetLastError();
@@ -1089,11 +1356,11 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
                 // the pattern-only instantiations need the same opt-in shared memory size; if that fails, stay general
                 cudaError_t cp = cudaSuccess;
                 if (h->persist_threads == lsp::PT_SMALL)
-                    cp = cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false, lsp::PT_SMALL / 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    cp = cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false, lsp::PT_SMALL / 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
                 else if (res)
-                    cp = cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false, lsp::PWARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    cp = cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 1, false, lsp::PWARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
                 else
-                    cp = cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 0, false, lsp::PWARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    cp = cudaFuncSetAttribute(lsp::pcg_persistent_kernel<3, 0, false, lsp::PWARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
                 if (cp != cudaSuccess) {
                     cudaGetLastError();
                     h->pat_on = 0;
@@ -1109,6 +1376,12 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
                 cudaGetLastError();   // not fatal: the graph path stays available
             }
         }
+    }
+    rc = configure_fused(h, di, 3, &h->fused[0]);
+    if (rc) return fail(rc);
+    if (k_max >= 4) {
+        rc = configure_fused(h, di, 4, &h->fused[1]);
+        if (rc) return fail(rc);
     }
     if (hflags & 8) {
         ls_set_error("perm_new2old is not a permutation of [0, V)");
@@ -1144,6 +1417,16 @@ extern "C" int ls_pcg_solve(void *handle, const float *b, float *x, const float 
         case 3: return solve_k<3>(h, b, x, x0, rtol, maxit, info_dev, info_host, stream);
         default: return solve_k<4>(h, b, x, x0, rtol, maxit, info_dev, info_host, stream);
     }
+}
+
+extern "C" int ls_pcg_set_refinement(void *handle, int max_restarts, float theta) {
+    PcgHandle *h = (PcgHandle *)handle;
+    LS_REQUIRE(h != nullptr, "handle is NULL");
+    LS_REQUIRE(max_restarts >= 0 && max_restarts <= 8, "max_restarts must be in [0, 8]");
+    LS_REQUIRE(theta >= 1.0f && theta < 1e6f, "theta must be >= 1");
+    h->refine = max_restarts;
+    h->theta = theta;
+    return LS_OK;
 }
 
 extern "C" int ls_pcg_destroy(void *handle) {
@@ -1237,6 +1520,18 @@ extern "C" int ls_pcg_phase_cycles(void *handle, int64_t *out, int n, void *stre
 extern "C" int ls_pcg_describe(void *handle, int64_t *out8) {
     PcgHandle *h = (PcgHandle *)handle;
     LS_REQUIRE(h != nullptr && out8 != nullptr, "NULL pointer");
+    const PcgHandle::FusedCfg &fc = h->fused[0];
+    if (fc.on) {   // fused two-synchronisation solver: [engine, padded entries, grid, cluster size, mode 10 + RES, grid, threads, re-ordered]
+        out8[0] = fc.pat ? 2 : 1;
+        out8[1] = h->sell_entries;
+        out8[2] = fc.grid;
+        out8[3] = fc.cluster;
+        out8[4] = 10 + fc.res;
+        out8[5] = fc.grid;
+        out8[6] = fc.nw * 32;
+        out8[7] = h->has_perm;
+        return LS_OK;
+    }
     out8[0] = (h->pat_on && h->persist_on) ? 2 : h->sell_on;   // 2 = pattern-only SELL-32 in the persistent kernel, 1 = SELL-32 engine, 0 = TMA-staged CSR engine
     out8[1] = h->sell_entries;            // padded entries of the SELL copy
     out8[2] = h->sell_on ? h->sell_grid : h->spmm_grid;

@@ -32,7 +32,7 @@ namespace lsp {
 constexpr int PT = LS_PT;   // 24 warps: 85 registers per thread (1024 threads forced spills into the SpMM loop)
 constexpr int PWARPS = PT / 32;
 constexpr int PT_SMALL = 256;   // CTAs that own <= 16 slices (mid-size meshes): cheaper CTA barriers, no spills
-constexpr int NVMAX = 12;
+constexpr int NVMAX = 16;   // values per all-reduce (the fused kernel reduces 4 K <= 16 at a restart)
 
 struct GridBar {
     unsigned int count;

@@ -175,6 +175,178 @@ __global__ void __launch_bounds__(SELL_THREADS, 1) spmm_sell_kernel(const SellAr
     }
 }
 
+// ---- TMA-staged variant: the entry stream goes HBM -> shared memory through per-warp rings of 1-D bulk copies ----------
+// The register-prefetch kernel above keeps 24 warps x 2 KB of matrix stream in flight per SM and spends 16 registers per
+// thread on it; it is latency-bound (ncu at V = 1e6: warps active 37 %, long-scoreboard 16 stalls/issue, DRAM 58 % busy).
+// Here every warp owns a private ring of DEPTH slots of 2 KB in shared memory.  Lane 0 issues one cp.async.bulk per slice
+// (the first <= 8 entry columns of a slice are 256 w contiguous bytes) DEPTH slices ahead; completion is counted on one
+// mbarrier per slot.  Only the owning warp ever touches its slots, so there is no CTA-level synchronisation and no
+// "empty" barrier: a slot is refilled by the same warp right after it has issued the gathers that consumed its column
+// indices (those gathers cannot issue before the LDS results exist).  NW x DEPTH x 2 KB = 192 KB of matrix stream in
+// flight per SM, no prefetch registers, so 32 warps fit.  Columns beyond the 8th of a wide slice (rare on meshes) are read
+// straight from global memory as before.  The kernel is PDL-aware: it lets the next kernel of the stream start its own
+// matrix prefetch early (griddepcontrol.launch_dependents) and touches the vectors only after griddepcontrol.wait.
+constexpr int SELL_SLOT_BYTES = 2048;   // 8 entry columns x 32 lanes x 8 bytes
+
+inline size_t sell_tma_smem_bytes(int nw, int depth) {
+    return (size_t)nw * depth * SELL_SLOT_BYTES + (size_t)nw * depth * 8 + 2048;   // rings, mbarriers, reduction scratch
+}
+
+template <int K, bool DOT, int NW, int DEPTH>
+__global__ void __launch_bounds__(NW * 32, 1) spmm_sell_tma_kernel(const SellArgs a) {
+    typedef typename PRow<K>::T PT;
+    constexpr int U = 8;
+    extern __shared__ __align__(128) unsigned char sm_raw[];
+    int2 *ring = reinterpret_cast<int2 *>(sm_raw);                                         // [NW][DEPTH][256]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm_raw + (size_t)NW * DEPTH * SELL_SLOT_BYTES);   // [NW][DEPTH]
+    double *red = reinterpret_cast<double *>(sm_raw + (size_t)NW * DEPTH * SELL_SLOT_BYTES + (size_t)NW * DEPTH * 8);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int s_begin = (int)((long long)a.nslices * cta / G);
+    const int s_end = (int)((long long)a.nslices * (cta + 1) / G);
+    const PT *__restrict__ prow = reinterpret_cast<const PT *>(a.p);
+    int2 *myring = ring + (size_t)warp * DEPTH * 256;
+    uint64_t *mybar = bars + warp * DEPTH;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) ls_mbar_init(mybar + d, 1);
+    }
+    ls_fence_mbar_init();
+    __syncwarp();
+
+    // this warp's slices: s_begin + warp + i NW, i = 0 .. n - 1
+    const int n = (s_end - s_begin - warp + NW - 1) / NW;   // may be <= 0
+    // slice offsets, 32 slices at a time: lane l holds soff of slice i0 + l and of its successor
+    int win_i0 = 0, so0 = 0, so1 = 0;
+    auto load_window = [&](int i0) {
+        const int i = i0 + lane;
+        if (i < n) {
+            const int s = s_begin + warp + i * NW;
+            so0 = a.soff[s];
+            so1 = a.soff[s + 1];
+        } else {
+            so0 = so1 = 0;
+        }
+        win_i0 = i0;
+    };
+    uint64_t policy = ls_policy_evict_first();
+    auto issue = [&](int i) {   // warp-uniform; window must cover i
+        const int o0 = __shfl_sync(0xffffffffu, so0, i - win_i0), o1 = __shfl_sync(0xffffffffu, so1, i - win_i0);
+        const int w = (o1 - o0) >> 5;
+        const int cw = w < U ? w : U;
+        if (lane == 0) {
+            uint64_t *bar = mybar + (i % DEPTH);
+            ls_mbar_expect_tx(bar, (uint32_t)(cw * 256));
+            if (cw > 0) ls_bulk_g2s_hint(myring + (size_t)(i % DEPTH) * 256, a.ent + o0, (uint32_t)(cw * 256), bar, policy);
+        }
+    };
+    if (n > 0) {
+        load_window(0);
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d)
+            if (d < n) issue(d);
+    }
+    // the matrix never changes between launches; the vectors do: wait for the previous kernel before touching them
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (a.done != nullptr && *reinterpret_cast<const volatile int *>(a.done) != 0) {
+        // converged earlier in this graph chunk: nothing to do, but the bulk copies already in flight must land before the
+        // CTA (and its shared memory) goes away
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d)
+            if (d < n) ls_mbar_wait(mybar + d, 0u);
+        return;
+    }
+
+    double dacc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) dacc[k] = 0.0;
+
+    // consumer side needs the offsets of slice i (window A) while the producer side runs DEPTH ahead (window B = so0/so1)
+    int c_i0 = 0, c0 = 0, c1 = 0;
+    auto load_cwindow = [&](int i0) {
+        const int i = i0 + lane;
+        if (i < n) {
+            const int s = s_begin + warp + i * NW;
+            c0 = a.soff[s];
+            c1 = a.soff[s + 1];
+        } else {
+            c0 = c1 = 0;
+        }
+        c_i0 = i0;
+    };
+    if (n > 0) load_cwindow(0);
+    for (int i = 0; i < n; ++i) {
+        if (i - c_i0 >= 32) load_cwindow(i);
+        const int s = s_begin + warp + i * NW;
+        const int row = s * 32 + lane;
+        const int o0 = __shfl_sync(0xffffffffu, c0, i - c_i0), o1 = __shfl_sync(0xffffffffu, c1, i - c_i0);
+        const int w = (o1 - o0) >> 5;
+        const int slot = i % DEPTH;
+        ls_mbar_wait(mybar + slot, (uint32_t)((i / DEPTH) & 1));
+        const int2 *e_s = myring + (size_t)slot * 256 + lane;
+        int2 cv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) cv[u] = (u < w) ? e_s[u * 32] : make_int2(row, 0);
+        float acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.f;
+        {
+            PT xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = prow[cv[u].x];
+            // the gathers above could only issue once every LDS of this slot had returned: the slot is free, refill it
+            __syncwarp();
+            if (i + DEPTH < n) {
+                if (i + DEPTH - win_i0 >= 32) load_window(i + DEPTH);
+                issue(i + DEPTH);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float xk[K];
+                prow_get(xv[u], xk);
+                const float wv = __int_as_float(cv[u].y);
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = fmaf(wv, xk[k], acc[k]);
+            }
+        }
+        const int2 *e = a.ent + o0 + lane;
+        for (int j = U; j < w; j += U) {   // wide slices: remaining columns straight from global memory
+#pragma unroll
+            for (int u = 0; u < U; ++u) cv[u] = (j + u < w) ? ld_entry(e + (j + u) * 32) : make_int2(row, 0);
+            PT xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = prow[cv[u].x];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float xk[K];
+                prow_get(xv[u], xk);
+                const float wv = __int_as_float(cv[u].y);
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = fmaf(wv, xk[k], acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) a.y[(size_t)k * a.ldy + row] = acc[k];
+        if (DOT) {
+            float xr[K];
+            prow_get(prow[row], xr);
+#pragma unroll
+            for (int k = 0; k < K; ++k) dacc[k] += (double)xr[k] * (double)acc[k];
+        }
+    }
+    if (DOT) {
+        double tot[K];
+        const bool last = ls_grid_reduce<K>(dacc, tot, a.partials, a.ticket, red, tid, NW * 32, 1, cta, G);
+        if (last && tid == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) a.dot_out[k] = tot[k];
+        }
+    }
+}
+
 // ---- SELL build (from the solver's CSR copy) ---------------------------------------------------------
 // widths: one warp per slice, w = max row length; cnt[s] = 32 w
 static __global__ void sell_width_kernel(int V, int nslices, const int *__restrict__ rowptr, int *__restrict__ cnt) {

@@ -1,4 +1,5 @@
-"""ctypes binding of libls_b200.so (the C ABI declared in include/largesteps_b200.h).
+"""ctypes binding of libls_b200.so (the C ABI declared in include/largesteps_b200.h; timing harnesses and per-phase
+counters in include/largesteps_b200_diag.h).
 
 There is NO CPU / torch fallback: if the shared library is missing the import of any operator fails loudly with
 instructions to build it (`python -c "import __graft_entry__ as g; g.build()"` or `make -C csrc`).
@@ -15,7 +16,7 @@ LIB_PATH = os.environ.get("LS_LIB_PATH") or os.path.join(_HERE, "libls_b200.so")
 LS_OK, LS_ERR_BAD_ARG, LS_ERR_CUDA, LS_ERR_BREAKDOWN, LS_ERR_NOT_CONVERGED, LS_ERR_UNSUPPORTED, \
     LS_ERR_INDEX_RANGE, LS_ERR_WORKSPACE = range(8)
 
-# every symbol include/largesteps_b200.h declares: name -> (restype, argtypes)
+# every symbol include/largesteps_b200.h and largesteps_b200_diag.h declare: name -> (restype, argtypes)
 SYMBOLS = {
     "ls_version": (c_int, []),
     "ls_last_error": (c_char_p, []),
@@ -36,6 +37,7 @@ SYMBOLS = {
     "ls_pcg_solve": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p,
                              POINTER(c_float), c_void_p]),
     "ls_pcg_destroy": (c_int, [c_void_p]),
+    "ls_pcg_set_refinement": (c_int, [c_void_p, c_int, c_float]),
     "ls_pcg_bench_spmm": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "ls_pcg_spmm_bytes": (c_int64, [c_void_p, c_int]),
     "ls_pcg_describe": (c_int, [c_void_p, POINTER(c_int64)]),

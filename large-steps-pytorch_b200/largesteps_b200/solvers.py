@@ -49,11 +49,15 @@ class PCGSolver(Solver):
                      compute_matrix (pure data-layout change: b and x stay in the caller's vertex numbering)
     check : bool     True: every solve synchronises, raises Breakdown / NotConverged (or warns).  False: the solve is
                      fully asynchronous on the current stream (one kernel launch, no host round trip); status and
-                     iteration count are read lazily (`.iterations`, `.status`, `.raise_for_status()`).
+                     iteration count are read lazily (`.iterations`, `.status`, `.raise_for_status()`), and a solve that
+                     hit `maxit` or broke down is reported by a RuntimeWarning at the next call (never blocking).
+    refine : int     accuracy guard (ls_pcg_set_refinement): after convergence the true residual b - M x is evaluated
+                     with fp64 accumulation and the iteration restarts from it, at most `refine` times, if it sits more
+                     than `theta` times above the floor fp32 storage of x imposes.  0 switches the check off.
     """
 
     def __init__(self, M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, strict=False, reorder=True,
-                 check=True):
+                 check=True, refine=1, theta=3.0):
         if precond not in ("jacobi", "none"):
             raise ValueError(f"Unknown preconditioner '{precond}'.")
         rowptr, col, val = csr_of(M)
@@ -69,8 +73,10 @@ class PCGSolver(Solver):
         self.guess_fwd = None
         self.guess_bwd = None
         self._info_host = (ctypes.c_float * 8)()
-        self._info_dev = None        # device-side info of the last asynchronous solve
+        self._info_dev = None        # info of the last asynchronous solve: pinned host memory the kernel writes into
+        self._info_event = None
         self._info_stale = False
+        self._unreported = False     # an asynchronous solve whose status nobody has looked at yet
         self._handle = ctypes.c_void_p(0)
         lib = N.lib()
         with torch.cuda.device(self.device):
@@ -80,6 +86,7 @@ class PCGSolver(Solver):
             N.check(lib.ls_pcg_create(ctypes.byref(self._handle), self.V, self.nnz, N.ptr(rowptr), N.ptr(col),
                                       N.ptr(val), N.ptr(order), 1 if precond == "jacobi" else 0, K_MAX, N.ptr(self._ws),
                                       nbytes.value, N.stream_ptr(self.device)), "ls_pcg_create")
+            N.check(lib.ls_pcg_set_refinement(self._handle, int(refine), float(theta)), "ls_pcg_set_refinement")
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -91,12 +98,31 @@ class PCGSolver(Solver):
             self._handle = ctypes.c_void_p(0)
 
     # -- stats of the last solve ------------------------------------------------------------------------
-    def _sync_info(self):
-        if self._info_stale:     # asynchronous solve: fetch [iterations, status, relres...] now (synchronises)
-            host = self._info_dev.cpu()
+    def _sync_info(self, block=True):
+        """Fetch [iterations, status, relres..., restarts] of the last asynchronous solve.  block=False: only if the
+        solve has already finished (returns False otherwise)."""
+        if self._info_stale:
+            if block:
+                self._info_event.synchronize()
+            elif not self._info_event.query():
+                return False
             for j in range(8):
-                self._info_host[j] = float(host[j])
+                self._info_host[j] = float(self._info_dev[j])
             self._info_stale = False
+        return True
+
+    def _report_previous(self):
+        # the reference's direct solve cannot fail to converge; this iterative one can (maxit, breakdown on a non-SPD
+        # matrix): say so at the next call instead of staying silent, without ever blocking the stream
+        if self._unreported and self._sync_info(block=False):
+            self._unreported = False
+            st = int(self._info_host[1])
+            if st == 2:
+                warnings.warn(f"{type(self).__name__}: the previous solve stopped at maxit={self.maxit} "
+                              f"(relres {[float(self._info_host[2 + j]) for j in range(3)]})", RuntimeWarning)
+            elif st == 3:
+                warnings.warn(f"{type(self).__name__}: the previous solve broke down after {int(self._info_host[0])} iterations "
+                              "(matrix not SPD, or NaN in the right-hand side)", RuntimeWarning)
 
     @property
     def iterations(self):
@@ -112,7 +138,14 @@ class PCGSolver(Solver):
     def status(self):
         """0/1 converged, 2 iteration cap reached, 3 breakdown (not SPD / NaN) -- of the last solve."""
         self._sync_info()
+        self._unreported = False
         return int(self._info_host[1])
+
+    @property
+    def restarts(self):
+        """restarts from the true residual the last solve needed (see `refine`)."""
+        self._sync_info()
+        return int(self._info_host[6])
 
     def raise_for_status(self):
         st = self.status
@@ -124,8 +157,15 @@ class PCGSolver(Solver):
     def describe(self):
         out = (ctypes.c_int64 * 8)()
         N.check(N.lib().ls_pcg_describe(self._handle, out), "ls_pcg_describe")
+        o = [int(v) for v in out]
+        if o[4] >= 10:    # fused two-synchronisation solver (csrc/ls_pcg_fused.cuh)
+            return {"algo": "fused", "sell_engine": o[0], "sell_entries": o[1], "grid": o[2], "cluster": o[3],
+                    "residency": o[4] - 10, "threads": o[6], "reordered": o[7],
+                    "persistent": 2 if o[4] - 10 >= 1 else 1, "persistent_grid": o[2]}
         keys = ("sell_engine", "sell_entries", "spmm_grid", "vec_grid", "persistent", "persistent_grid", "planned", "reordered")
-        return dict(zip(keys, [int(v) for v in out]))
+        d = dict(zip(keys, o))
+        d["algo"] = "classic" if d["persistent"] else "graph"
+        return d
 
     def phase_cycles(self, per_cta=False):
         g = self.describe()["persistent_grid"] if per_cta else 0
@@ -133,7 +173,10 @@ class PCGSolver(Solver):
         out = (ctypes.c_int64 * n)()
         with torch.cuda.device(self.device):
             N.check(N.lib().ls_pcg_phase_cycles(self._handle, out, n, N.stream_ptr(self.device)), "ls_pcg_phase_cycles")
-        keys = ("spmm", "reduce1", "update", "reduce2", "pupdate", "barrier3", "_", "iterations")
+        if self.describe()["algo"] == "fused":
+            keys = ("phaseA", "sync_ps", "phaseB", "sync_rz", "restart", "_0", "_", "iterations")
+        else:
+            keys = ("spmm", "reduce1", "update", "reduce2", "pupdate", "barrier3", "_", "iterations")
         d = dict(zip(keys, [int(v) for v in out[:8]]))
         if per_cta:
             d["per_cta"] = [[int(out[8 + 8 * c + j]) for j in range(8)] for c in range(g)]
@@ -157,6 +200,7 @@ class PCGSolver(Solver):
             raise TypeError(f"b must be float32, got {b.dtype}")
         if b.shape[0] != self.V:
             raise ValueError(f"b has {b.shape[0]} rows, the system matrix has {self.V}")
+        self._report_previous()
         b = b.detach().contiguous()
         k = b.shape[1]
         x0 = None
@@ -185,11 +229,14 @@ class PCGSolver(Solver):
                     else:
                         N.check(rc, "ls_pcg_solve")
                 else:
-                    if self._info_dev is None:
-                        self._info_dev = torch.zeros(8, dtype=torch.float32, device=self.device)
+                    if self._info_dev is None:   # mapped pinned host memory: the kernel's last store lands here, no copy is queued
+                        self._info_dev = torch.zeros(8, dtype=torch.float32).pin_memory()
+                        self._info_event = torch.cuda.Event()
                     N.check(lib.ls_pcg_solve(self._handle, N.ptr(bb), N.ptr(xx), N.ptr(gg), kk, self.rtol, self.maxit,
                                              N.ptr(self._info_dev), None, st), "ls_pcg_solve")
+                    self._info_event.record(torch.cuda.current_stream(self.device))
                     self._info_stale = True
+                    self._unreported = True
                 if k > K_MAX:
                     x[:, k0:k0 + kk] = xx
         if self.warm_start:
@@ -215,8 +262,8 @@ class CholeskySolver(PCGSolver):
     One asynchronous kernel launch per solve (`check=False`); `.raise_for_status()` checks the last solve on demand."""
 
     def __init__(self, M):
-        # like cholespy's solve, the call is asynchronous and has no failure path: NaN in -> NaN out
-        super().__init__(M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, check=False)
+        # like cholespy's solve, the call is asynchronous; a solve that did not converge is reported at the next call
+        super().__init__(M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, check=False, refine=1)
 
 
 class ConjugateGradientSolver(PCGSolver):

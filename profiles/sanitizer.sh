@@ -23,11 +23,11 @@ for kw in (dict(lambda_=1.0, alpha=0.95), dict(lambda_=19.0, cotan=True)):
     err = np.linalg.norm(x.detach().cpu().numpy() - xd) / np.linalg.norm(xd)
     assert err < 1e-5, err
     opt = AdamUniform([u], lr=0.01); opt.step()
-torch.cuda.synchronize(); print("sanitizer case ok", os.environ.get("LS_PCG_MODE"), os.environ.get("LS_SPMM_ENGINE"))
+torch.cuda.synchronize(); print("sanitizer case ok", {k: v for k, v in os.environ.items() if k.startswith("LS_")})
 PY
 for tool in memcheck racecheck; do
-  # SAN_QUICK=1: persistent mode only (after a change confined to ls_pcg_persistent.cuh)
-  for mode in "LS_PCG_MODE=persistent" ${SAN_QUICK:+--} "LS_PCG_MODE=graph" "LS_PCG_MODE=graph LS_SPMM_ENGINE=csr"; do
+  # SAN_QUICK=1: fused solver only (one cluster, cooperative grid at three residency levels)
+  for mode in "LS_X=1" "LS_PCG_CLUSTER=0" "LS_PCG_CLUSTER=0 LS_PCG_RES=1" "LS_PCG_CLUSTER=0 LS_PCG_RES=0 LS_PCG_PATTERN=0" ${SAN_QUICK:+--} "LS_PCG_ALGO=classic" "LS_PCG_MODE=graph" "LS_PCG_MODE=graph LS_SPMM_ENGINE=csr"; do
     if [ "$mode" = "--" ]; then break; fi
     echo "=== $tool $mode"
     env $mode timeout 600 compute-sanitizer --tool $tool --error-exitcode 7 python /tmp/san_case.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitizer case ok|Error|hazard|access at" | head -12

@@ -9,13 +9,22 @@ import pytest
 from conftest import ROOT
 import largesteps_b200._native as N
 
-HEADER = os.path.join(ROOT, "include", "largesteps_b200.h")
+HEADERS = [os.path.join(ROOT, "include", "largesteps_b200.h"), os.path.join(ROOT, "include", "largesteps_b200_diag.h")]
 
 
-def declared_symbols():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ls_[a-z0-9_]+)\s*\(", src)))
+def declared_symbols(headers=HEADERS):
+    names = set()
+    for h in headers:
+        src = open(h).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(ls_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_diagnostics_are_not_in_the_product_header():
+    prod = declared_symbols(HEADERS[:1])
+    for n in ("ls_pcg_bench", "ls_pcg_bench_spmm", "ls_pcg_phase_cycles"):
+        assert n not in prod and n in declared_symbols(HEADERS[1:])
 
 
 def test_library_is_built_and_loads():

@@ -73,21 +73,37 @@ def test_plane_alpha(alpha):
     M = compute_matrix(*to_dev(v, f), **kw)
     s = PCGSolver(M)
     assert rel_l2(s.solve(t(b)).cpu().numpy(), ds.solve(b)) < BAR
-    assert 0 < s.iterations < 2000 and max(s.relres[:3]) <= 1.01e-7
+    assert 0 < s.iterations < 2000 and max(s.relres[:3]) <= 5e-5
     assert rel_l2(s.solve(t(g), backward=True).cpu().numpy(), ds.solve(g)) < BAR
 
 
-def test_ill_conditioned_alpha_0999():
-    """alpha = 0.999 (figures/influence/generate_data.py:28), kappa ~ 1.2e4: the stress case."""
-    v, f = workloads.plane(200, seed=0)
+@pytest.mark.parametrize("n", [200, 500])
+def test_ill_conditioned_alpha_0999(n):
+    """alpha = 0.999 (figures/influence/generate_data.py:28), kappa ~ 1.2e4: the stress case.  The north-star bar (1e-5)
+    holds here too: the solve restarts from the fp64-accumulated true residual when the recursive one has drifted."""
+    v, f = workloads.plane(n, seed=0)
     kw = dict(lambda_=1.0, alpha=0.999)
     (r, c, val, V), ds = direct_for(v, f, kw)
     _, b, g = rhs(r, c, val, V, v)
     M = compute_matrix(*to_dev(v, f), **kw)
-    s = PCGSolver(M, rtol=3e-8)
+    s = PCGSolver(M)
     err = rel_l2(s.solve(t(b)).cpu().numpy(), ds.solve(b))
-    assert err < 5e-5, err           # fp32 floor at this conditioning; reported, see DESIGN.md
-    assert s.iterations < 5000
+    print(f"alpha=0.999 n={n}: fwd err {err:.2e}, iterations {s.iterations}, restarts {s.restarts}")
+    assert err < BAR, err
+    assert s.iterations < 5000 and s.restarts <= 1
+    errb = rel_l2(s.solve(t(g), backward=True).cpu().numpy(), ds.solve(g))
+    print(f"alpha=0.999 n={n}: bwd err {errb:.2e}, iterations {s.iterations}, restarts {s.restarts}")
+    assert errb < BAR, errb
+    # the default plug-in (what from_differential uses) takes the same path
+    u = t(b).requires_grad_(True)
+    x = from_differential(M, u)
+    (x * t(g)).sum().backward()
+    assert rel_l2(x.detach().cpu().numpy(), ds.solve(b)) < BAR and rel_l2(u.grad.cpu().numpy(), ds.solve(g)) < BAR
+    # without the guard the recurrence-carried s = A p may drift past the bar over ~600 iterations: documented, not asserted
+    s0 = PCGSolver(M, refine=0)
+    e0 = rel_l2(s0.solve(t(b)).cpu().numpy(), ds.solve(b))
+    print(f"alpha=0.999 n={n}: refine=0 err {e0:.2e}, iterations {s0.iterations}")
+    assert e0 < 1e-4
 
 
 @pytest.mark.parametrize("k", [1, 2, 4, 6])
@@ -192,38 +208,94 @@ def test_morton_reorder_is_transparent(bunny_mesh):
     assert rc == N.LS_ERR_BAD_ARG and "permutation" in N.last_error()
 
 
-@pytest.mark.parametrize("env", [
-    {},                                   # default: persistent kernel, r/Ap in shared memory, fixed-point all-reduce
-    {"LS_PCG_RES": "0"},                  # persistent kernel, r/Ap in global memory
-    {"LS_PCG_FASTRED": "0"},              # persistent kernel, fenced partial-array all-reduce
-    {"LS_PCG_FASTRED": "11"},             # fast all-reduce for 11 reductions, then the fenced one takes over mid-solve
-    {"LS_PCG_MODE": "graph"},             # CUDA graph of 3 kernels per iteration, SELL SpMM engine
-    {"LS_PCG_MODE": "graph", "LS_SPMM_ENGINE": "csr"},   # ... with the TMA-staged CSR SpMM engine
-    {"LS_FORCE_REORDER": "1"},            # Morton re-ordered private copy
-])
+MODES = [
+    {},                                                         # default: fused kernel; cluster for these sizes, pattern copy if uniform
+    {"LS_PCG_CLUSTER": "0"},                                    # fused, cooperative grid, everything in shared memory (256-thread CTAs)
+    {"LS_PCG_CLUSTER": "0", "LS_PCG_SMALLCTA": "0"},            # ... 768-thread CTAs
+    {"LS_PCG_CLUSTER": "0", "LS_PCG_RES": "1"},                 # ... x / p in global memory
+    {"LS_PCG_CLUSTER": "0", "LS_PCG_RES": "0"},                 # ... every vector in global memory
+    {"LS_PCG_CLUSTER": "0", "LS_PCG_FASTRED": "0"},             # fenced partial-array all-reduce only
+    {"LS_PCG_CLUSTER": "0", "LS_PCG_FASTRED": "11"},            # fast all-reduce for 11 reductions, then the fenced one takes over mid-solve
+    {"LS_PCG_CLUSTER": "4"},                                    # one cluster of 4 / 8 CTAs (meshes that do not fit fall back to the grid)
+    {"LS_PCG_CLUSTER": "8"},
+    {"LS_PCG_PATTERN": "0"},                                    # general matrix copy even for uniform Laplacians
+    {"LS_PCG_REFINE": "0"},                                     # no true-residual check
+    {"LS_PCG_ALGO": "classic"},                                 # round-1 three-synchronisation persistent kernel
+    {"LS_PCG_ALGO": "classic", "LS_PCG_RES": "0"},
+    {"LS_PCG_MODE": "graph"},                                   # CUDA graph of 3 kernels per iteration, SELL SpMM engine (TMA-staged)
+    {"LS_PCG_MODE": "graph", "LS_SELL_TMA": "0"},               # ... register-prefetch SELL kernel
+    {"LS_PCG_MODE": "graph", "LS_SPMM_ENGINE": "csr"},          # ... with the TMA-staged CSR SpMM engine
+    {"LS_FORCE_REORDER": "1"},                                  # Morton re-ordered private copy
+]
+
+
+@pytest.mark.parametrize("env", MODES, ids=lambda e: ",".join(f"{k[3:]}={v}" for k, v in e.items()) or "default")
 def test_every_solver_mode_meets_the_bar(env, bunny_mesh, monkeypatch):
     """All execution modes of the solve (selected at handle creation) give the direct-solve answer."""
     for k_, v_ in env.items():
         monkeypatch.setenv(k_, v_)
-    cases = [config2(bunny_mesh), (*workloads.plane(260, seed=1), dict(lambda_=1.0, alpha=0.95))]
+    cases = [config2(bunny_mesh), (*workloads.plane(260, seed=1), dict(lambda_=1.0, alpha=0.95)),
+             (*workloads.icosphere(5), dict(lambda_=10.0))]
     for v, f, kw in cases:
         (r, c, val, V), ds = direct_for(v, f, kw)
         _, b, g = rhs(r, c, val, V, v)
         M = compute_matrix(*to_dev(v, f), **kw)
         s = PCGSolver(M)
         d = s.describe()
+        uniform = not kw.get("cotan")
         if env.get("LS_PCG_MODE") == "graph":
-            assert d["persistent"] == 0
-        elif env.get("LS_PCG_RES") == "0":
-            assert d["persistent"] == 1
+            assert d["algo"] == "graph" and d["persistent"] == 0
+            assert d["sell_engine"] == (0 if env.get("LS_SPMM_ENGINE") == "csr" else 1)
+        elif env.get("LS_PCG_ALGO") == "classic":
+            assert d["algo"] == "classic" and d["persistent"] == (1 if env.get("LS_PCG_RES") == "0" else 2)
         else:
-            assert d["persistent"] == 2
-        assert d["sell_engine"] == (0 if env.get("LS_SPMM_ENGINE") == "csr" else 1)
+            assert d["algo"] == "fused"
+            assert d["sell_engine"] == (2 if uniform and env.get("LS_PCG_PATTERN") != "0" else 1)
+            if env.get("LS_PCG_CLUSTER") == "0":
+                assert d["cluster"] == 0 and d["grid"] > 16
+                assert d["residency"] == int(env.get("LS_PCG_RES", "2"))
+                assert d["threads"] == (768 if env.get("LS_PCG_SMALLCTA") == "0" or d["residency"] < 2 else 256)
+            elif "LS_PCG_CLUSTER" in env:
+                assert d["cluster"] in (0, int(env["LS_PCG_CLUSTER"]))
+                if V < 20000:
+                    assert d["cluster"] == int(env["LS_PCG_CLUSTER"])
+            else:
+                assert d["cluster"] == 16 and d["residency"] == 2
         if "LS_FORCE_REORDER" in env:
             assert d["reordered"] == 1
-        assert rel_l2(s.solve(t(b)).cpu().numpy(), ds.solve(b)) < BAR
-        assert rel_l2(s.solve(t(g), backward=True).cpu().numpy(), ds.solve(g)) < BAR
-        assert 0 < s.iterations < 1000 and max(s.relres[:3]) <= 1.01e-7
+        assert rel_l2(s.solve(t(b)).cpu().numpy(), ds.solve(b)) < BAR, (env, kw)
+        assert 0 < s.iterations < 1000 and max(s.relres[:3]) <= 5e-5     # relres is the TRUE residual once the guard has run
+        assert rel_l2(s.solve(t(g), backward=True).cpu().numpy(), ds.solve(g)) < BAR, (env, kw)
+        # warm start through the same path (the reference CG plug-in's behaviour, solvers.py:102-110)
+        w = PCGSolver(M, warm_start=True)
+        x1 = w.solve(t(b))
+        it_cold = w.iterations
+        b2 = (b + 1e-3 * np.random.default_rng(7).normal(size=b.shape)).astype(np.float32)
+        assert rel_l2(w.solve(t(b2)).cpu().numpy(), ds.solve(b2)) < BAR, (env, kw)
+        assert w.iterations < it_cold
+
+
+def test_two_live_solvers_of_different_size():
+    """Handles of different sizes share kernel functions: the opt-in shared-memory attribute of a function must never
+    be lowered by a later, smaller handle.  Interleave solves of a big and a small mesh."""
+    big_v, big_f = workloads.plane(700, seed=0)
+    small_v, small_f = workloads.plane(330, seed=0)
+    kw = dict(lambda_=1.0, alpha=0.95)
+    Mb = compute_matrix(*to_dev(big_v, big_f), **kw)
+    sb = PCGSolver(Mb)
+    Ms = compute_matrix(*to_dev(small_v, small_f), **kw)
+    ss = PCGSolver(Ms)
+    db, dsm = sb.describe(), ss.describe()
+    assert db["algo"] == "fused" and dsm["algo"] == "fused"
+    (rs, cs, vals, Vs), ds_small = direct_for(small_v, small_f, kw)
+    bs = np.random.default_rng(0).normal(size=(Vs, 3)).astype(np.float32)
+    tvb = to_dev(big_v, big_f)[0]
+    for _ in range(2):
+        xb = sb.solve(to_differential(Mb, tvb))
+        xs = ss.solve(t(bs))
+        assert rel_l2(xb.cpu().numpy(), big_v) < BAR
+        assert rel_l2(xs.cpu().numpy(), ds_small.solve(bs)) < BAR
+    assert sb.describe() == db and ss.describe() == dsm      # neither fell back to another path
 
 
 def test_deterministic_bitwise():
@@ -341,7 +413,7 @@ def test_full_size_roundtrip_adjoint_linearity():
     # round trip: from_differential(M, to_differential(M, v)) == v
     v2 = s.solve(to_differential(M, tv))
     assert rel_l2(v2.cpu().numpy(), v) < BAR
-    assert s.iterations < 400 and max(s.relres[:3]) <= 1.01e-7
+    assert s.iterations < 400 and max(s.relres[:3]) <= 5e-5
     # true residual of a random solve, measured with torch's own sparse matmul in fp64-ish
     b = torch.randn(V, 3, device=DEV)
     x = s.solve(b)
@@ -358,6 +430,53 @@ def test_full_size_roundtrip_adjoint_linearity():
     assert rel_l2(x2.cpu().numpy(), (2.0 * x + y).cpu().numpy()) < BAR
 
 
+@pytest.fixture(scope="module")
+def direct_1m():
+    """fp64 SuperLU factorisation of BASELINE config 3's matrix (V = 1e6): ~25-60 s on one host core, done once."""
+    v, f = workloads.plane(1000, seed=0)
+    kw = dict(lambda_=1.0, alpha=0.95)
+    (r, c, val, V), ds = direct_for(v, f, kw)
+    return v, f, kw, (r, c, val, V), ds
+
+
+def test_full_size_forward_backward_vs_direct(direct_1m):
+    """BASELINE config 3 at full size against the oracle itself: forward and backward (O(1) and 1e-4 gradients)."""
+    v, f, kw, (r, c, val, V), ds = direct_1m
+    _, b, g = rhs(r, c, val, V, v)
+    M = compute_matrix(*to_dev(v, f), **kw)
+    u = t(b).requires_grad_(True)
+    x = from_differential(M, u)
+    e_fwd = rel_l2(x.detach().cpu().numpy(), ds.solve(b))
+    errs = [e_fwd]
+    for scale in (1.0, 1e-4):
+        u.grad = None
+        gg = (scale * g).astype(np.float32)
+        x = from_differential(M, u)
+        (x * t(gg)).sum().backward()
+        errs.append(rel_l2(u.grad.cpu().numpy(), ds.solve(gg)))
+    print("1M fwd / bwd / bwd 1e-4 rel-L2 vs fp64 direct:", ["%.2e" % e for e in errs])
+    assert max(errs) < BAR, errs
+    # the warm-started plug-in at full size
+    w = ConjugateGradientSolver(M)
+    w.solve(t(b))
+    b2 = (b + 1e-3 * np.random.default_rng(7).normal(size=b.shape)).astype(np.float32)
+    assert rel_l2(w.solve(t(b2)).cpu().numpy(), ds.solve(b2)) < BAR
+
+
+def test_config4_quarter_million_uniform_vs_direct():
+    """BASELINE config 4's mesh (plane 500^2, uniform, alpha = 0.95) against the fp64 direct solve, forward and backward."""
+    v, f = workloads.plane(500, seed=5)
+    kw = dict(lambda_=1.0, alpha=0.95)
+    (r, c, val, V), ds = direct_for(v, f, kw)
+    _, b, g = rhs(r, c, val, V, v)
+    M = compute_matrix(*to_dev(v, f), **kw)
+    u = t(b).requires_grad_(True)
+    x = from_differential(M, u)
+    (x * t(g)).sum().backward()
+    assert rel_l2(x.detach().cpu().numpy(), ds.solve(b)) < BAR
+    assert rel_l2(u.grad.cpu().numpy(), ds.solve(g)) < BAR
+
+
 def test_four_million_vertices_roundtrip():
     """Largest size exercised: plane 2000^2 (V = 4e6, nnz = 27,984,002).  r/Ap no longer fit in shared memory, so the
     persistent kernel runs with them in global memory (RES = 0); round trip + true residual."""
@@ -366,7 +485,7 @@ def test_four_million_vertices_roundtrip():
     M = compute_matrix(tv, tf, 1.0, alpha=0.95)
     assert M._nnz() == 7 * 2000 * 2000 - 8 * 2000 + 2
     s = PCGSolver(M)
-    assert s.describe()["persistent"] == 1
+    assert s.describe()["residency"] == 0
     x = s.solve(to_differential(M, tv))
     assert rel_l2(x.cpu().numpy(), v) < BAR
     b = torch.randn(M.shape[0], 3, device=DEV)
