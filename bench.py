@@ -10,10 +10,15 @@ workload : BASELINE config 3 -- plane 1000x1000 (V = 1,000,000, nnz(M) = 6,992,0
            no collective on the solve path; NCCL only gathers a checksum at the end.
 value    : whole-job solves/s with the right-hand sides already in HBM (CUDA events, max over ranks)
 e2e      : same through the public API with HOST (pinned) buffers: H2D of u and D2H of v inside the timed region
-roofline : the in-solver SpMM+dot kernel timed alone with CUDA events, rotating over 4 copies of the matrix and
-           vectors (336 MB > 126 MB L2) so every launch streams from HBM; algorithmic bytes 8 nnz + 4 (V+1) + 8 k V
-cpu_baseline / --impl reference : the oracle's direct solve (SuperLU fp32, symmetric mode -- the stand-in for the
-           reference's cholespy/CHOLMOD CholeskySolver, which is not installable offline), factorisation untimed.
+roofline : the HBM figure of record is the SpMV (BASELINE metric part 2): the stand-alone in-solver SpMM+dot kernel timed
+           alone with CUDA events, rotating over 4 copies of matrix + vectors (336 MB > 126 MB L2) so every launch streams
+           from HBM; algorithmic bytes 8 nnz + 4 (V+1) + 8 k V.  The solve kernel (one launch per solve, the
+           dominant kernel of the timed region) is reported beside it as `solve_kernel`: it is L2-resident by construction
+           (pattern-only matrix copy + shared-memory residency), so its DRAM traffic -- measured by ncu, source file named --
+           is far below any algorithmic byte model and an HBM fraction would be meaningless; its byte model and time are given.
+cpu_baseline / --impl reference : the reference's path on the box's host cores: the C/OpenMP port of its
+           ConjugateGradientSolver (threads chosen around the cgroup CPU quota, median of 3) and the SuperLU direct solve that
+           stands in for its default cholespy/CHOLMOD CholeskySolver (1 core, factorisation untimed); the faster one is `value`.
 """
 import argparse
 import json
@@ -117,24 +122,6 @@ class ClockSampler:
         return out
 
 
-def cpu_direct_baseline(v, f, kw, b_list, solves):
-    """Oracle leg: SuperLU fp32 direct solve on this box's host cores (factorisation untimed)."""
-    import oracle
-    t0 = time.perf_counter()
-    r, c, val, V = oracle.compute_matrix(v, f, **kw)
-    t_asm = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    ds = oracle.DirectSolver(r, c, val, V, dtype=np.float32)
-    t_fac = time.perf_counter() - t0
-    ts, x = [], None
-    for i in range(solves):
-        b = b_list[i % len(b_list)]
-        t0 = time.perf_counter()
-        x = ds.solve(b)
-        ts.append(time.perf_counter() - t0)
-    return dict(t_assembly_s=t_asm, t_factor_s=t_fac, t_solve_s=ts, factor_nnz=ds.factor_nnz, x_last=x, solver=ds)
-
-
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -145,35 +132,72 @@ def cpu_model():
     return "unknown"
 
 
+def shared_config(wl_name, wl, V, nnz):
+    """Identical in both arms, so that the driver can tell they ran the same workload."""
+    return {"workload": wl_name, "desc": wl["desc"], "V": int(V), "nnz": int(nnz), "rhs_columns": 3, "rtol": RTOL,
+            "l2": "4 rotating right-hand sides; the GPU solve's working set is L2-resident by design (pattern-only matrix "
+                  "copy), the stand-alone SpMV is timed HBM-cold by rotating 4 matrix+vector copies (336 MB > 126 MB L2)"}
+
+
+def cpu_reference_leg(v, f, kw, bs, repeats=3, warm=False):
+    """The reference's solve path on this box's host cores, both ports, each `repeats` times (median + spread):
+       (a) C/OpenMP port of ConjugateGradientSolver (oracle/cg_port.c; abs tol 1e-5 as in the reference), threads chosen
+           around the cgroup CPU quota and pinned; cold start unless `warm` (the reference keeps its previous solution),
+       (b) SuperLU fp32 symmetric-mode direct solve, 1 core, factorisation untimed: stand-in for cholespy/CHOLMOD."""
+    import oracle
+    from oracle.cport import CPortCG, host_cpu_budget, pin_to_allowed_cores
+    budget = host_cpu_budget()
+    r, c, val, V = oracle.compute_matrix(v, f, **kw)
+    cg = CPortCG(r, c, val, V)
+    cg.autotune_threads(bs[1 % len(bs)])
+    pinned = pin_to_allowed_cores(cg.threads)
+    cg.guess_fwd = None
+    cg.solve(bs[1 % len(bs)])                   # untimed: first-touch page faults, thread pool
+    t_cgs = []
+    for i in range(repeats):
+        if not warm:
+            cg.guess_fwd = None
+        t0 = time.perf_counter()
+        cg.solve(bs[i % len(bs)])
+        t_cgs.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    ds = oracle.DirectSolver(r, c, val, V, dtype=np.float32)
+    t_fac = time.perf_counter() - t0
+    t_dss = []
+    for i in range(repeats):
+        t0 = time.perf_counter()
+        ds.solve(bs[i % len(bs)])
+        t_dss.append(time.perf_counter() - t0)
+    med = statistics.median
+    return {"cg": cg, "ds": ds, "V": V, "nnz": len(val), "t_cg": t_cgs, "t_ds": t_dss, "t_fac": t_fac, "budget": budget,
+            "pinned_cpus": len(pinned) if pinned else None,
+            "record": {"reference_cg_port": {"solves_per_s": 1.0 / med(t_cgs), "median_s": med(t_cgs), "min_s": min(t_cgs),
+                                             "max_s": max(t_cgs), "cores": cg.threads, "iterations_per_axis": cg.iters,
+                                             "note": "oracle/cg_port.c: C/OpenMP restatement of the reference CG (fp32, absolute tol 1e-5), "
+                                                     + ("warm starts" if warm else "cold start")},
+                       "direct_solve": {"solves_per_s": 1.0 / med(t_dss), "median_s": med(t_dss), "min_s": min(t_dss),
+                                        "max_s": max(t_dss), "cores": 1, "factor_s": t_fac, "factor_nnz": ds.factor_nnz,
+                                        "note": "scipy SuperLU fp32 symmetric mode: stand-in for cholespy/CHOLMOD (not installable offline)"},
+                       "cpu": cpu_model(), "host_cores": os.cpu_count(), "affinity_cpus": budget["affinity_cpus"],
+                       "cgroup_cpu_max": budget["cgroup_cpu_max"], "quota_cores": budget["quota_cores"],
+                       "pinned_cpus": len(pinned) if pinned else None}}
+
+
 def run_reference(args, wl, wl_name):
     """CPU arm: the reference's path restated on the host (the reference itself is Python + an un-installable wheel).
-    Two ports exist: (a) the direct solve that stands in for its default CholeskySolver (SuperLU, 1 core), (b) its
-    ConjugateGradientSolver in C with OpenMP on all host threads (oracle/cg_port.c), warm starts as in the reference.
-    Both are timed once; the faster one runs the K timed steps."""
+    Both CPU ports are measured (median of 3); the faster one runs the K timed steps.  The SuperLU figure is printed every time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     v, f, kw = build_mesh(wl, seed=0)
     import oracle
-    from oracle.cport import CPortCG
     r, c, val, V = oracle.compute_matrix(v, f, **kw)
     A = oracle.coo_to_scipy(r, c, val, V, dtype=np.float32)
     rng = np.random.default_rng(100)
     bs = [(A @ (v + rng.normal(0, 0.01, v.shape).astype(np.float32))).astype(np.float32) for _ in range(2)]
-    cg = CPortCG(r, c, val, V)
-    cg.autotune_threads(bs[1])            # untimed: the thread count that actually runs fastest under this box's CPU quota
-    cg.guess_fwd = None
-    cg.solve(bs[1])                       # untimed: first-touch page faults
-    cg.guess_fwd = None
-    t0 = time.perf_counter()
-    cg.solve(bs[0])
-    t_cg = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    ds = oracle.DirectSolver(r, c, val, V, dtype=np.float32)
-    t_fac = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    ds.solve(bs[0])
-    t_ds = time.perf_counter() - t0
+    leg = cpu_reference_leg(v, f, kw, bs, repeats=3, warm=True)
+    cg, ds = leg["cg"], leg["ds"]
+    t_cg, t_ds = statistics.median(leg["t_cg"]), statistics.median(leg["t_ds"])
     use_cg = t_cg < t_ds
     step = (lambda i: cg.solve(bs[i % 2])) if use_cg else (lambda i: ds.solve(bs[i % 2]))
     for i in range(args.warmup):
@@ -185,18 +209,17 @@ def run_reference(args, wl, wl_name):
     val_sps = args.steps / dt
     cores = cg.threads if use_cg else 1
     sample = (f"{args.steps} solves of a (V,3) fp32 RHS at V={V} with the faster of two CPU ports of the reference: "
-              f"{'C/OpenMP port of its ConjugateGradientSolver (abs tol 1e-5, warm starts) on ' + str(cg.threads) + ' threads' if use_cg else 'SuperLU direct solve (stand-in for cholespy/CHOLMOD), 1 core'}"
-              f"; single-solve probes: CG port {t_cg:.3f} s, direct {t_ds:.3f} s after an untimed {t_fac:.1f} s factorisation")
+              f"{'C/OpenMP port of its ConjugateGradientSolver (abs tol 1e-5, warm starts) on ' + str(cg.threads) + ' pinned threads' if use_cg else 'SuperLU direct solve (stand-in for cholespy/CHOLMOD), 1 core'}"
+              f"; probes (median of 3): CG port {t_cg:.3f} s, direct {t_ds:.3f} s after an untimed {leg['t_fac']:.1f} s factorisation")
+    cb = dict(leg["record"])
+    cb.update({"value": val_sps, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample})
     line = {
         "impl": "reference", "metric": METRIC, "value": val_sps, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl_name, "desc": wl["desc"], "rhs_columns": 3,
-                   "solver": "CPU port of the reference path: " + ("ConjugateGradientSolver (C/OpenMP)" if use_cg else "direct solve (SuperLU)")},
-        "cpu_baseline": {"value": val_sps, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample,
-                         "cpu": cpu_model(), "host_cores": os.cpu_count(), "factor_s": t_fac,
-                         "cg_port_single_solve_s": t_cg, "direct_single_solve_s": t_ds,
-                         "cg_iterations_per_axis": cg.iters},
+        "config": shared_config(wl_name, wl, V, len(val)),
+        "solver": "CPU port of the reference path: " + ("ConjugateGradientSolver (C/OpenMP)" if use_cg else "direct solve (SuperLU)"),
+        "cpu_baseline": cb,
         "e2e": {"value": val_sps, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -228,11 +251,12 @@ def run_b200(args, wl, wl_name):
     V = v.shape[0]
     tv = torch.from_numpy(v).to(dev)
     tf = torch.from_numpy(f).to(dev)
-    M = compute_matrix(tv, tf, **kw)              # first call pays library / context warm-up
+    M = compute_matrix(tv, tf, **kw)              # first call pays library / context warm-up and the allocator's first cudaMallocs
     torch.cuda.synchronize()
+    del M                                         # as in a remesh: the old matrix is dropped, its blocks return to torch's caching allocator
     t0 = time.perf_counter()
-    M = compute_matrix(tv, tf, **kw)              # steady-state assembly time (what a re-parameterisation after remesh costs)
-    torch.cuda.synchronize()
+    M = compute_matrix(tv, tf, **kw)              # steady-state assembly time (round 1 timed this with the first M still alive:
+    torch.cuda.synchronize()                      #  ~250 MB of fresh cudaMalloc inside the timed region, 28.6 ms instead of ~2 ms)
     t_assemble = time.perf_counter() - t0
     nnz = M._nnz()
     R = 4
@@ -312,22 +336,50 @@ def run_b200(args, wl, wl_name):
     e2e_value = world * args.steps / (ms_e2e * 1e-3)
     bytes_io = V * 3 * 4
 
+    # ---- BASELINE config 4: 8 independent 250K-vertex meshes, mesh i -> rank i mod N, aggregate solves/s -----------
+    cfg4 = None
+    if not args.no_config4:
+        wl4 = WORKLOADS["plane500"]
+        mine = D.assign(8, rank, world)
+        items = []
+        for i in mine:
+            v4, f4, kw4 = build_mesh(wl4, seed=i)
+            t4 = torch.from_numpy(v4).to(dev)
+            M4 = compute_matrix(t4, torch.from_numpy(f4).to(dev), **kw4)
+            u4 = (to_differential(M4, t4) + 0.01 * torch.randn(t4.shape[0], 3, device=dev, generator=gen)).contiguous()
+            from_differential(M4, u4, "Cholesky")
+            items.append((M4, u4, v4))
+        reps4 = 10
+
+        def step4(i):
+            with torch.no_grad():
+                for (M4, u4, _) in items:
+                    from_differential(M4, u4, "Cholesky")
+
+        ms4, _ = timed(step4, reps4, 3)
+        with torch.no_grad():
+            err4 = max(float((from_differential(M4, to_differential(M4, torch.from_numpy(v4).to(dev)), "Cholesky").cpu()
+                              - torch.from_numpy(v4)).norm() / torch.from_numpy(v4).norm()) for (M4, _, v4) in items[:1]) if items else 0.0
+        cfg4 = {"workload": "plane500", "desc": wl4["desc"], "meshes": 8, "meshes_per_rank": len(mine),
+                "solves_per_s": 8 * reps4 / (ms4 * 1e-3), "ms_per_round_of_8": ms4 / reps4,
+                "roundtrip_rel_l2_first_mesh": err4,
+                "how": "each rank solves its share of the 8 meshes back to back; CUDA events, max over ranks; no collective on the solve path"}
+        del items
+
     # ---- roofline ---------------------------------------------------------------------------------------------
-    # dominant kernel = the persistent solve kernel (one launch per solve): algorithmic bytes per launch = CG
-    # iterations x the per-iteration figure of SURVEY.md 8(d) (SpMM 8 nnz + 4 (V+1) + 8 k V, update 72 MB + 4 MB diag,
-    # p-update 36 MB at V = 1e6: 195.9 MB), divided by the solve's device time from the timed region above.
-    # `spmv` next to it: the stand-alone in-solver SpMM+dot kernel timed alone (CUDA events over 400 launches issued
-    # from C, rotating over 4 copies of matrix + vectors = 336 MB > L2, so every launch streams from HBM).
+    # HBM figure of record: the stand-alone in-solver SpMM+dot kernel (BASELINE metric part 2), CUDA events over 400 launches
+    # issued from C, rotating over 4 copies of matrix + vectors = 336 MB > L2, so every launch streams from HBM.
+    # The solve kernel (dominant kernel of the timed region, one launch per solve) is described beside it.
     roof = None
+    extra_more = {}
     if rank == 0:
         from largesteps_b200.solvers import bench_kernels
         desc = solver.describe()
         peak, peak_src = measured_peak()
         k = 3
         b_spmm = solver.spmm_bytes(k)
-        b_iter = b_spmm + (6 * k) * 4 * V + 4 * V + (3 * k) * 4 * V
-        extra = [PCGSolver(M) for _ in range(3)]
-        handles = [solver] + extra
+        extra_h = [PCGSolver(M) for _ in range(3)]
+        handles = [solver] + extra_h
         L = 400
 
         def time_kernels(which, hs):
@@ -342,49 +394,65 @@ def run_b200(args, wl, wl_name):
 
         us_cold = time_kernels(0, handles)
         us_hot = time_kernels(0, handles[:1])
-        spmv = {"kernel": "lsk::spmm_sell_kernel<3,DOT>" if desc["sell_engine"] else "lsk::spmm_tma_kernel<3,...>",
-                "algorithmic_bytes": b_spmm, "us_per_launch": us_cold, "achieved_GBs": b_spmm / (us_cold * 1e-6) / 1e9,
-                "frac": b_spmm / (us_cold * 1e-6) / 1e9 / peak, "l2_resident_us_per_launch": us_hot,
-                "how": "CUDA events over 400 back-to-back launches from C rotating over 4 matrix+vector copies (336 MB > L2)"}
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "solve_traffic.json")
+        spmv_kernel = "lsk::spmm_sell_tma_kernel<3,DOT,32,3> (SELL-32 entry stream staged by cp.async.bulk into per-warp rings)"
+        if os.environ.get("LS_SELL_TMA") == "0":
+            spmv_kernel = "lsk::spmm_sell_kernel<3,DOT>"
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
         if os.path.exists(tp) and wl_name == "plane1000":
             try:
-                traffic = json.load(open(tp))["dram_bytes_per_launch"]
+                tj = json.load(open(tp))
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
             except Exception:
-                traffic = None
+                pass
+        roof = {"bound": "hbm", "achieved": b_spmm / (us_cold * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": b_spmm / (us_cold * 1e-6) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": spmv_kernel, "algorithmic_bytes": b_spmm, "us_per_launch": us_cold, "l2_resident_us_per_launch": us_hot,
+                "peak_source": peak_src,
+                "how": "CUDA events over 400 back-to-back launches from C (programmatic dependent launch) rotating over 4 matrix+vector "
+                       "copies (336 MB > L2); bytes = 8 nnz + 4 (V+1) + 8 k V (SURVEY 8d)"}
+        # the solve kernel: L2-resident by design -- say so with numbers instead of an HBM fraction
         t_solve_s = ms_total * 1e-3 / args.steps
-        if desc["persistent"]:
-            ach = it_mean * b_iter / t_solve_s / 1e9
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "kernel": "lsp::pcg_persistent_kernel<3,RES=%d> (whole solve, 1 launch)" % (desc["persistent"] - 1),
-                    "algorithmic_bytes": it_mean * b_iter, "algorithmic_bytes_per_iteration": b_iter,
-                    "us_per_launch": 1e6 * t_solve_s, "peak_source": peak_src,
-                    "how": "solve time from the timed region (CUDA events, device-resident RHS); bytes = CG iterations x "
-                           "SURVEY 8(d) per-iteration bytes; r/Ap/dinv stay in shared memory, so DRAM traffic is lower",
-                    "spmv": spmv}
-        else:
-            roof = {"bound": "hbm", "achieved": spmv["achieved_GBs"], "peak": peak, "unit": "GB/s", "frac": spmv["frac"],
-                    "traffic": traffic, "kernel": spmv["kernel"], "algorithmic_bytes": b_spmm,
-                    "us_per_launch": us_cold, "peak_source": peak_src, "how": spmv["how"], "spmv": spmv}
-        roof["solver"] = desc
+        pat = desc.get("sell_engine") == 2
+        b_iter = (4 * (nnz - V) + 4 * V if pat else 8 * nnz) + 32 * V + 48 * V     # matrix stream, z write+gather, p and x read+write
+        st_traffic, st_src = None, None
+        tp2 = os.path.join(ROOT, "profiles", "solve_traffic.json")
+        if os.path.exists(tp2) and wl_name == "plane1000":
+            try:
+                tj = json.load(open(tp2))
+                st_traffic, st_src = tj["dram_bytes_per_launch"], tj.get("source")
+            except Exception:
+                pass
+        roof["solve_kernel"] = {
+            "kernel": "lsf::pcg_fused_kernel<3,RES=%d,...> (whole solve, 1 launch)" % desc.get("residency", -1) if desc.get("algo") == "fused"
+                      else "lsp::pcg_persistent_kernel (round-1 kernel)",
+            "us_per_launch": 1e6 * t_solve_s, "cg_iterations": it_mean, "us_per_iteration": 1e6 * t_solve_s / max(it_mean, 1),
+            "bound": "L2 / latency (working set L2-resident: pattern-only matrix copy 4 B/entry, r/s/D^-1 in shared memory)",
+            "algorithmic_bytes_per_iteration": b_iter, "algorithmic_GBs": it_mean * b_iter / t_solve_s / 1e9,
+            "dram_bytes_per_launch": st_traffic, "dram_traffic_source": st_src,
+            "note": "algorithmic_GBs may exceed the HBM peak because the data never leaves L2; it is NOT an HBM roofline fraction",
+            "solver": desc}
         if wl_name == "plane1000" and not args.no_spmv_4m:
-            # the >= 70 % SpMV claim must be about DRAM, so measure the same kernel on a plane whose working
-            # set is far beyond L2 (2000 x 2000: V = 4e6, 336 MB per launch); one handle, no rotation needed
+            # the same kernel on a plane whose working set is far beyond L2 (2000 x 2000: V = 4e6, 336 MB per launch)
             v4, f4, kw4 = build_mesh(WORKLOADS["plane2000"], seed=0)
             tv4, tf4 = torch.from_numpy(v4).to(dev), torch.from_numpy(f4).to(dev)
             M4 = compute_matrix(tv4, tf4, **kw4)
             s4 = PCGSolver(M4)
             us4 = time_kernels(0, [s4])
             b4 = s4.spmm_bytes(k)
-            roof["spmv_4M"] = {"workload": WORKLOADS["plane2000"]["desc"], "kernel": spmv["kernel"], "algorithmic_bytes": b4,
-                               "us_per_launch": us4, "achieved_GBs": b4 / (us4 * 1e-6) / 1e9,
-                               "frac": b4 / (us4 * 1e-6) / 1e9 / peak,
+            with torch.no_grad():
+                s4.solve(to_differential(M4, tv4))
+                t0 = time.perf_counter()
+                s4.solve(to_differential(M4, tv4))
+                torch.cuda.synchronize()
+                t4m = time.perf_counter() - t0
+            roof["spmv_4M"] = {"workload": WORKLOADS["plane2000"]["desc"], "algorithmic_bytes": b4, "us_per_launch": us4,
+                               "achieved_GBs": b4 / (us4 * 1e-6) / 1e9, "frac": b4 / (us4 * 1e-6) / 1e9 / peak,
+                               "solve_ms": 1e3 * t4m, "solve_iterations": s4.iterations,
                                "how": "CUDA events over 400 back-to-back launches from C; 336 MB per launch >> 126 MB L2"}
             del s4, M4, tv4, tf4
-        if desc["persistent"]:
-            # in-solver SpMM phase, from the kernel's own per-phase cycle counters (profiling instantiation of the same
-            # kernel, CTA 0): the SpMV as it actually runs inside the solve (Ap stays in shared memory, p comes from L2)
+        if desc.get("persistent"):
+            # per-phase SM cycles of the solve kernel (profiling instantiation of the same kernel, CTA 0)
             os.environ["LS_PCG_PROFILE"] = "1"
             try:
                 solver.solve(us[0])
@@ -392,17 +460,79 @@ def run_b200(args, wl, wl_name):
             finally:
                 del os.environ["LS_PCG_PROFILE"]
             itn = max(pc["iterations"], 1)
-            roof["phase_cycles_per_iteration"] = {kk: round(vv / itn) for kk, vv in pc.items() if kk not in ("_", "iterations")}
-        del extra, handles
+            roof["solve_kernel"]["phase_cycles_per_iteration"] = {kk: round(vv / itn) for kk, vv in pc.items() if kk not in ("_", "_0", "iterations")}
+        del extra_h, handles
+
+        # ---- the other BASELINE configs and the section 8(f) rows, so that the driver sees them -----------------------
+        def solve_ms(Mx, ux, reps=50):
+            sx = _cache[(id(Mx), "Cholesky")][0] if (id(Mx), "Cholesky") in _cache else None
+            with torch.no_grad():
+                from_differential(Mx, ux, "Cholesky")
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    from_differential(Mx, ux, "Cholesky")
+                e1.record()
+                torch.cuda.synchronize()
+            sx = _cache[(id(Mx), "Cholesky")][0]
+            return e0.elapsed_time(e1) / reps, sx.iterations, sx.describe()
+
+        for cname, wname in (("config1_icosphere", "icosphere"), ("config2_bunny", "bunny")):
+            vv_, ff_, kw_ = build_mesh(WORKLOADS[wname], seed=0)
+            tvx, tfx = torch.from_numpy(vv_).to(dev), torch.from_numpy(ff_).to(dev)
+            Mx = compute_matrix(tvx, tfx, **kw_)
+            ux = (to_differential(Mx, tvx) + 0.01 * torch.randn(tvx.shape[0], 3, device=dev, generator=gen)).contiguous()
+            msx, itx, dx = solve_ms(Mx, ux)
+            extra_more[cname] = {"V": int(tvx.shape[0]), "solve_ms": msx, "iterations": itx, "us_per_iteration": 1e3 * msx / max(itx, 1),
+                                 "cluster": dx.get("cluster"), "grid": dx.get("grid")}
+            if wname == "bunny":
+                # config 5 stand-in: Tutorial-shaped loop (two solves + fused AdamUniform per step, no renderer) at 52.8K
+                from largesteps_b200.optimize import AdamUniform
+                target = (tvx * (1.0 + 0.3 * torch.sin(3 * tvx[:, :1]) * torch.cos(2 * tvx[:, 1:2]))).detach()
+                uu = to_differential(Mx, tvx).clone().requires_grad_(True)
+                opt = AdamUniform([uu], lr=0.01)
+
+                def loop(n):
+                    for _ in range(n):
+                        xx = from_differential(Mx, uu, "Cholesky")
+                        loss = ((xx - target) ** 2).mean()
+                        opt.zero_grad()
+                        loss.backward()
+                        opt.step()
+
+                loop(20)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                loop(500)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                extra_more["config5_loop_standin"] = {"V": int(tvx.shape[0]), "steps": 500, "it_per_s": 500 / dt,
+                                                      "note": "from_differential -> MSE loss -> backward -> AdamUniform; no renderer (nvdiffrast needs GL)"}
+            del Mx
+        # re-parameterisation after a remesh (8 f4): assemble + solver build + first solve, arena reused
+        from largesteps_b200.remesh import Reparameterizer
+        for nm, nplane in (("250K", 500), ("1M", 1000)):
+            vv_, ff_ = build_mesh(WORKLOADS["plane500" if nplane == 500 else "plane1000"], seed=3)[:2]
+            tvx, tfx = torch.from_numpy(vv_).to(dev), torch.from_numpy(ff_).to(dev)
+            rp = Reparameterizer(lambda_=1.0, alpha=0.95)
+            Mx, ux = rp.update(tvx, tfx)                      # first call sizes the arena
+            with torch.no_grad():
+                from_differential(Mx, ux)
+            ts = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                Mx, ux = rp.update(tvx, tfx)
+                with torch.no_grad():
+                    from_differential(Mx, ux)
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            extra_more["reparameterize_" + nm] = {"ms_median": 1e3 * statistics.median(ts), "ms_min": 1e3 * min(ts),
+                                                  "what": "Reparameterizer.update (assembly + to_differential + solver build) + first from_differential, wall clock"}
+            del rp, Mx, ux
 
     clocks = sampler.stop() if rank == 0 else None
-    if rank == 0 and roof and "phase_cycles_per_iteration" in roof:
-        mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        cyc = roof["phase_cycles_per_iteration"]["spmm"]
-        us_ph = cyc / mhz
-        roof["spmv_in_solver"] = {"us_per_iteration": us_ph, "sm_mhz": mhz, "algorithmic_bytes": roof["spmv"]["algorithmic_bytes"],
-                                  "achieved_GBs": roof["spmv"]["algorithmic_bytes"] / (us_ph * 1e-6) / 1e9,
-                                  "note": "SpMM phase of the persistent kernel (SM cycles of CTA 0 / SM clock); Ap never leaves shared memory"}
 
     # ---- trivial gather (the only collective): checksum of every rank's last solution ---------------------
     with torch.no_grad():
@@ -414,56 +544,36 @@ def run_b200(args, wl, wl_name):
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         b_host = [us[0].cpu().numpy(), us[1].cpu().numpy()]
-        nsolve = 3 if V >= 500000 else 10
-        cb = cpu_direct_baseline(v, f, kw, b_host, nsolve)
-        best = min(cb["t_solve_s"])
-        parity = float(np.linalg.norm(xs.cpu().numpy().astype(np.float64) - cb["solver"].solve(b_host[0]).astype(np.float64))
-                       / np.linalg.norm(cb["x_last"].astype(np.float64)))
-        # the reference's other plug-in (ConjugateGradientSolver, solvers.py:41-126): C/OpenMP port on all host threads,
-        # cold start (guesses reset) like the GPU solves it stands next to; best of 3
-        from oracle.cport import CPortCG
-        import oracle as _o
-        rc_ = _o.compute_matrix(v, f, **kw)
-        cgp = CPortCG(rc_[0], rc_[1], rc_[2], rc_[3])
-        cgp.autotune_threads(b_host[1])   # untimed: the thread count that actually runs fastest under this box's CPU quota
-        cgp.guess_fwd = None
-        cgp.solve(b_host[1])              # untimed: first-touch page faults
-        t_cgs = []
-        for _ in range(3):
-            cgp.guess_fwd = None
-            t0c = time.perf_counter()
-            cgp.solve(b_host[0])
-            t_cgs.append(time.perf_counter() - t0c)
-        t_cg = min(t_cgs)
-        use_cg = t_cg < best
-        cpu = {"value": max(1.0 / best, 1.0 / t_cg), "unit": "solves/s", "cores": cgp.threads if use_cg else 1, "kind": "port",
-               "direct_solve": {"solves_per_s": 1.0 / best, "cores": 1},
-               "reference_cg_port": {"solves_per_s": 1.0 / t_cg, "cores": cgp.threads, "iterations_per_axis": cgp.iters,
-                                     "note": "oracle/cg_port.c: C/OpenMP restatement of the reference CG (fp32, absolute tol 1e-5), cold start"},
-               "sample": (f"best single (V,3) fp32 solve at V={V} of the faster of two CPU ports: C/OpenMP port of the reference CG on "
-                          f"{cgp.threads} threads (best of 3: {t_cg:.3f} s) vs SuperLU direct solve, 1 core (best of {nsolve}: "
-                          f"{best:.3f} s after an untimed {cb['t_factor_s']:.1f} s factorisation; stand-in for cholespy/CHOLMOD)"),
-               "cpu": cpu_model(), "host_cores": os.cpu_count(), "factor_s": cb["t_factor_s"],
-               "assembly_s": cb["t_assembly_s"], "factor_nnz": cb["factor_nnz"]}
+        leg = cpu_reference_leg(v, f, kw, b_host, repeats=3, warm=False)
+        xd = leg["ds"].solve(b_host[0]).astype(np.float64)
+        parity = float(np.linalg.norm(xs.cpu().numpy().astype(np.float64) - xd) / np.linalg.norm(xd))
+        t_cg, t_ds = statistics.median(leg["t_cg"]), statistics.median(leg["t_ds"])
+        use_cg = t_cg < t_ds
+        cpu = dict(leg["record"])
+        cpu.update({"value": max(1.0 / t_cg, 1.0 / t_ds), "unit": "solves/s", "cores": leg["cg"].threads if use_cg else 1, "kind": "port",
+                    "sample": (f"median of 3 single (V,3) fp32 solves at V={V}: C/OpenMP port of the reference CG on {leg['cg'].threads} "
+                               f"pinned threads, cold start ({t_cg:.3f} s) vs SuperLU direct solve, 1 core ({t_ds:.3f} s after an untimed "
+                               f"{leg['t_fac']:.1f} s factorisation; stand-in for cholespy/CHOLMOD); the faster is `value`")})
 
     if rank == 0:
+        extra = {"fwd_bwd_pairs_per_s": pairs_per_s, "us_per_cg_iteration": 1e3 * (ms_total / args.steps) / max(it_mean, 1),
+                 "assembly_ms": 1e3 * t_assemble, "first_solve_incl_solver_build_ms": 1e3 * t_first,
+                 "parity_rel_l2_vs_cpu_direct": parity, "checksums": chk.flatten().tolist()[:6], "config4": cfg4}
+        extra.update(extra_more)
         line = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl_name, "desc": wl["desc"], "V": V, "nnz": nnz, "rhs_columns": 3,
-                       "solver": "Jacobi-PCG, cold start, persistent cooperative kernel", "rtol": RTOL, "cg_iterations_mean": it_mean,
-                       "parallelism": f"{world} independent mesh(es), one per GPU, no collective on the solve path",
-                       "l2": "per-iteration working set ~200 MB > 126 MB L2 and 4 rotating right-hand sides; no explicit flush"},
+            "config": shared_config(wl_name, wl, V, nnz),
+            "solver": "Jacobi-PCG, cold start, one fused persistent kernel per solve; cg_iterations_mean=%.1f; %d independent mesh(es), "
+                      "one per GPU, no collective on the solve path" % (it_mean, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,
-            "extra": {"fwd_bwd_pairs_per_s": pairs_per_s, "us_per_cg_iteration": 1e3 * (ms_total / args.steps) / max(it_mean, 1),
-                      "assembly_ms": 1e3 * t_assemble, "first_solve_incl_solver_build_ms": 1e3 * t_first,
-                      "parity_rel_l2_vs_cpu_direct": parity, "checksums": chk.flatten().tolist()[:6]},
+            "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:
@@ -480,6 +590,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("LS_BENCH_WORKLOAD", "plane1000"), choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spmv-4m", action="store_true", help="skip the 4M-vertex SpMV roofline measurement")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config-4 sub-record (8 x 250K meshes over the ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]

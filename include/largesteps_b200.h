@@ -126,6 +126,39 @@ int ls_pcg_describe(void *handle, int64_t *out8);
 /* algorithmic bytes of one in-solver SpMM launch: 8 nnz + 4 (V+1) + 8 k V  (SURVEY.md section 8 d)      */
 int64_t ls_pcg_spmm_bytes(void *handle, int k);
 
+/* ---- per-step glue either side of the solve  (replaces scripts/geometry.py:91-147 compute_face_normals /
+ *      compute_vertex_normals and the `v_unique[duplicate_idx]` gathers of scripts/main.py:176-180; csrc/ls_glue.cu) ---------
+ * All differentiable: the *_bwd entry points are the adjoints the Python autograd wrappers call.  Scatter-adds are gathers
+ * over a list built once per connectivity, so the per-step kernels use no atomics and are bit-reproducible.
+ *   faces (F,3) / idx (n): int32 (idx_bytes = 4) or int64 (8), device.  verts (V,3) float32.
+ *   ls_face_incidence: inc_ptr (V+1), inc (3F) int32: for vertex v the sorted codes 4*face + corner of its face corners.
+ *   ls_index_buckets:  ptr (V+1), items (n): positions i with idx[i] == v, sorted (the adjoint of a row gather).
+ *     both: workspace of ls_bucket_workspace_bytes(V) bytes; synchronise the stream; LS_ERR_INDEX_RANGE on a bad index.
+ *   ls_gather_rows_f32:      dst[i,:] = src[idx[i],:]               (n,k) <- (V,k), row-major contiguous
+ *   ls_gather_rows_bwd_f32:  gsrc[v,:] = sum_{i in bucket v} gdst[i,:]
+ *   ls_face_normals_f32:     n (3,F) = normalised cross(v1 - v0, v2 - v0), the reference's layout (geometry.py:104-110)
+ *   ls_vertex_normals_f32:   out (V,3) = normalised sum over incident corners of face_normal * acos(<d0,d1>), d0/d1 the corner's
+ *                            edge vectors divided by the Frobenius norm of the WHOLE edge field as in geometry.py:137-140;
+ *                            also writes raw_len (V) and edge_norms (3) for the backward.  scratch: ls_glue_scratch_bytes().  */
+int ls_glue_scratch_bytes(size_t *bytes_out);
+int ls_bucket_workspace_bytes(int64_t n_keys, size_t *bytes_out);
+int ls_face_incidence(const void *faces, int idx_bytes, int64_t F, int64_t V, int32_t *inc_ptr, int32_t *inc,
+                      void *workspace, size_t workspace_bytes, void *stream);
+int ls_index_buckets(const void *idx, int idx_bytes, int64_t n, int64_t V, int32_t *ptr, int32_t *items,
+                     void *workspace, size_t workspace_bytes, void *stream);
+int ls_gather_rows_f32(const float *src, const void *idx, int idx_bytes, int64_t n, int k, float *dst, void *stream);
+int ls_gather_rows_bwd_f32(const float *gdst, const int32_t *ptr, const int32_t *items, int64_t V, int k, float *gsrc, void *stream);
+int ls_face_normals_f32(const float *verts, const void *faces, int idx_bytes, int64_t F, float *n, void *stream);
+int ls_face_normals_bwd_f32(const float *verts, const void *faces, int idx_bytes, int64_t F, int64_t V,
+                            const int32_t *inc_ptr, const int32_t *inc, const float *gn, float *gverts, void *stream);
+int ls_vertex_normals_f32(const float *verts, const void *faces, int idx_bytes, int64_t F, int64_t V,
+                          const int32_t *inc_ptr, const int32_t *inc, const float *face_normals, float *out,
+                          float *raw_len, float *edge_norms, void *scratch, void *stream);
+int ls_vertex_normals_bwd_f32(const float *verts, const void *faces, int idx_bytes, int64_t F, int64_t V,
+                              const int32_t *inc_ptr, const int32_t *inc, const float *face_normals, const float *out,
+                              const float *raw_len, const float *edge_norms, const float *gout, float *gverts,
+                              float *gface_normals, void *scratch, void *stream);
+
 /* ---- fused AdamUniform step  (replaces largesteps/optimize.py:17-41) ----------------------------------
  *   n elements float32; one_minus_beta{1,2} = 1 - beta and c1 = 1 - beta1^t, c2 = 1 - beta2^t are computed by
  *   the caller in double (as the reference's Python does) and rounded once to float.

@@ -720,9 +720,23 @@ int launch_iteration(PcgHandle *h, cudaStream_t s) {
     return LS_OK;
 }
 
+// host-side resources only the graph-mode solver needs: created on its first use (they cost ~0.3 ms at handle creation)
+int graph_host_resources(PcgHandle *h) {
+    if (h->cap_stream) return LS_OK;
+    LS_CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    LS_CUDA_TRY(cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming));
+    LS_CUDA_TRY(cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming));
+    LS_CUDA_TRY(cudaMallocHost((void **)&h->pinned_done, 64));
+    return LS_OK;
+}
+
 template <int K>
 int build_graph(PcgHandle *h) {
     if (h->graph[K]) return LS_OK;
+    {
+        const int rc0 = graph_host_resources(h);
+        if (rc0) return rc0;
+    }
     cudaGraph_t g = nullptr;
     LS_CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
     int rc = LS_OK;
@@ -1169,13 +1183,10 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
         }                                                                                      \
     } while (0)
 
-    TRY_OR_FAIL(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
-    TRY_OR_FAIL(cudaEventCreateWithFlags(&h->ev[0], cudaEventDisableTiming));
-    TRY_OR_FAIL(cudaEventCreateWithFlags(&h->ev[1], cudaEventDisableTiming));
-    TRY_OR_FAIL(cudaMallocHost((void **)&h->pinned_done, 64));
-
-    // zero the whole workspace once (padding of every plane must be 0), then copy the CSR in
-    TRY_OR_FAIL(cudaMemsetAsync(workspace, 0, need, stream));
+    // zero what has to start at zero (vector planes incl. their padding rows, scalars, counters): NOT the matrix copies,
+    // which are written in full below -- at V = 1e6 that is ~100 MB of memset instead of ~500 MB
+    TRY_OR_FAIL(cudaMemsetAsync(h->dinv, 0, (size_t)((char *)h->soff - (char *)h->dinv), stream));
+    TRY_OR_FAIL(cudaMemsetAsync(h->perm, 0, (size_t)((char *)h->poff - (char *)h->perm), stream));
     h->has_perm = perm_new2old ? 1 : 0;
     if (perm_new2old && !getenv("LS_FORCE_REORDER")) {
         // keep the caller's numbering when it already gathers at least as coherently as the Morton order would
@@ -1184,7 +1195,17 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
         k_locality_score<<<gb > 2048 ? 2048 : gb, 256, 0, stream>>>(V, rowptr, col, sc);
         g_ls_launches.fetch_add(1);
         TRY_OR_FAIL(cudaGetLastError());
-        // score of the permuted order needs the permuted CSR: build it, score it, then decide
+        // a numbering whose neighbouring rows already gather from neighbouring columns (a grid, a remesher's output) is kept
+        // without ever building the permuted copy: fewer than 1 in 8 (row, slot) pairs break the coalescing
+        unsigned long long hs0 = 0;
+        TRY_OR_FAIL(cudaMemcpyAsync(&hs0, sc, sizeof(hs0), cudaMemcpyDeviceToHost, stream));
+        TRY_OR_FAIL(cudaStreamSynchronize(stream));
+        if (hs0 * 8ull <= (unsigned long long)nnz) {
+            perm_new2old = nullptr;
+            h->has_perm = 0;
+            TRY_OR_FAIL(cudaMemsetAsync(sc, 0, 16, stream));
+        }
+        // otherwise the score of the permuted order needs the permuted CSR: build it, score it, then decide
     }
     if (perm_new2old) {
         // internal copy in the caller's locality order: A' = P A P^T, rows re-sorted by new column

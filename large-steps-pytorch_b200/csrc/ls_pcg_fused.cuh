@@ -53,6 +53,11 @@ struct FusedArgs {
     float *r;               // K planes                  (RES = 0)
     float *s;               // K planes                  (RES = 0)
     float *z;               // published rows of 4 floats
+    float *z2;              // second row buffer (Chebyshev steps ping-pong between the two)
+    float *cy, *cd;         // Chebyshev iterate and direction, K planes each (owner-only)
+    int cheb_m;             // polynomial degree + 1 (<= 1: plain Jacobi);  z = q(D^-1 A) D^-1 r with m - 1 extra SpMVs
+    float cheb_c0;          // 1 / theta
+    float cheb_c1[8], cheb_c2[8];
     const float *b;         // (V,kb) caller layout
     float *out;             // (V,kb)
     const float *x0;        // warm start (V,kb) or NULL
@@ -331,6 +336,9 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
     auto P = [&](int li, int k, int row) -> float & { return RES == 2 ? p_s[((size_t)li * K + k) * 32 + lane] : a.pv[(size_t)k * Vp + row]; };
     auto Dv = [&](int li, int row) -> float { return RES ? d_s[(size_t)li * 32 + lane] : a.dinv[row]; };
 
+    float *zcur = a.z, *zalt = a.z2;   // the published vector lives in zcur; Chebyshev steps write the next iterate to zalt and swap
+    const int cheb_m = a.cheb_m;
+
     long long tA = 0, tS2 = 0, tB = 0, tS1 = 0, tX = 0, t0 = 0;
     const bool prof = PROF && (a.dbg != nullptr) && tid == 0;
 
@@ -356,6 +364,75 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
         S->e_grr[K + k] = er;
         S->skipA[k] = S->conv[k];
         S->skipB[k] = S->skipB[K + k] = S->conv[k];
+    };
+
+    // ---------------------------------------------------------------- Chebyshev polynomial preconditioner (precond = 2)
+    // z = q_{m-1}(D^-1 A) D^-1 r by the Chebyshev semi-iteration on [lambda_max / 30, lambda_max] (Gershgorin bound), y_1 = g / theta:
+    //   d_j = c1_j d_{j-1} + c2_j D^-1 (r - A y_j),  y_{j+1} = y_j + d_j .   Each step gathers the published iterate, so it costs one
+    // grid barrier but NO reduction: 2 all-reduces + (m - 1) barriers per m SpMVs instead of 2 all-reduces per SpMV.
+    // cheb_first: y_1 (from the residual already in R) -> zcur rows, cy / cd planes.   cheb_steps: the m - 1 gather steps; the last
+    // one accumulates r.z and r.r.  The caller's all-reduce publishes the final iterate.
+    auto cheb_first = [&]() {
+        for (int s = s_begin + warp; s < s_end; s += NW) {
+            const int li = s - s_begin, row = s * 32 + lane;
+            const float di = Dv(li, row) * a.cheb_c0;
+            float yy[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                yy[k] = di * R(li, k, row);
+                a.cy[(size_t)k * Vp + row] = yy[k];
+                a.cd[(size_t)k * Vp + row] = yy[k];
+            }
+            *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+        }
+    };
+    auto cheb_steps = [&](double (&acc2)[2 * K]) {
+        for (int j = 1; j < cheb_m; ++j) {
+            sync.barrier();                       // iterate j is visible everywhere
+            const float c1 = a.cheb_c1[j - 1], c2 = a.cheb_c2[j - 1];
+            const bool last = (j == cheb_m - 1);
+            for (int s = s_begin + warp; s < s_end; s += NW) {
+                const int li = s - s_begin, row = s * 32 + lane;
+                const int o0 = off_s[li], w = (off_s[li + 1] - o0) >> 5;
+                const int2 *e = a.ent + o0 + lane;
+                float t[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) t[k] = 0.f;
+                for (int jj = 0; jj < w; jj += 4) {
+                    int2 cv[4];
+                    float4 xg[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cv[u] = (jj + u < w) ? ld_ent<KEEP>(e + (jj + u) * 32) : make_int2(row, 0);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) xg[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float wv = __int_as_float(cv[u].y);
+                        const float xk[4] = {xg[u].x, xg[u].y, xg[u].z, xg[u].w};
+#pragma unroll
+                        for (int k = 0; k < K; ++k) t[k] = fmaf(wv, xk[k], t[k]);
+                    }
+                }
+                const float di = Dv(li, row);
+                float yy[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float rk = R(li, k, row);
+                    const float dn = fmaf(c1, a.cd[(size_t)k * Vp + row], c2 * (di * (rk - t[k])));
+                    yy[k] = a.cy[(size_t)k * Vp + row] + dn;
+                    a.cd[(size_t)k * Vp + row] = dn;
+                    a.cy[(size_t)k * Vp + row] = yy[k];
+                    if (last) {
+                        acc2[k] += (double)rk * (double)yy[k];
+                        acc2[K + k] += (double)rk * (double)rk;
+                    }
+                }
+                *reinterpret_cast<float4 *>(zalt + 4 * (size_t)row) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+            }
+            float *tz = zcur;
+            zcur = zalt;
+            zalt = tz;
+        }
     };
 
     // ---------------------------------------------------------------- cold start: x = 0, r = b, z = D^-1 b, p = s = 0
@@ -387,7 +464,16 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 acc[k] += (double)bv[k] * (double)zz[k];
                 acc[K + k] += (double)bv[k] * (double)bv[k];
             }
-            *reinterpret_cast<float4 *>(a.z + 4 * (size_t)row) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+            *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+        }
+        if (cheb_m > 1) {     // gamma = r . q(D^-1 A) D^-1 r instead of r . D^-1 r
+            double a2[2 * K];
+#pragma unroll
+            for (int i = 0; i < 2 * K; ++i) a2[i] = 0.0;
+            cheb_first();
+            cheb_steps(a2);
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = a2[k];
         }
         sync.template allreduce_slow<2 * K>(acc);     // fenced: also publishes z
         if (tid == 0) {
@@ -418,7 +504,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
             float xv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < K; ++k) xv[k] = X(li, k, row);
-            *reinterpret_cast<float4 *>(a.z + 4 * (size_t)row) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+            *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row) = make_float4(xv[0], xv[1], xv[2], xv[3]);
         }
         sync.barrier();
         double acc[4 * K];   // [gamma | rr | floor^2 | bb]
@@ -441,7 +527,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
 #pragma unroll
                 for (int u = 0; u < 4; ++u) cv[u] = (j + u < w) ? ld_ent<KEEP>(e + (j + u) * 32) : make_int2(row, 0);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) xg[u] = lsp::ld_coherent4(a.z + 4 * (size_t)cv[u].x);
+                for (int u = 0; u < 4; ++u) xg[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float wv = __int_as_float(cv[u].y);
@@ -474,6 +560,16 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 acc[2 * K + k] += (double)fl[k] * (double)fl[k];
                 acc[3 * K + k] += (double)bv[k] * (double)bv[k];
             }
+        }
+        if (cheb_m > 1) {     // preconditioned residual norm of the new residual (the gathers of the x rows end at the first barrier inside)
+            double a2[2 * K];
+#pragma unroll
+            for (int i = 0; i < 2 * K; ++i) a2[i] = 0.0;
+            sync.barrier();
+            cheb_first();
+            cheb_steps(a2);
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = a2[k];
         }
         sync.template allreduce_slow<4 * K>(acc);   // every CTA has finished gathering x rows once this returns
         if (tid == 0) {
@@ -524,7 +620,8 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                         P(li, k, row) = 0.f;
                     }
                 }
-                *reinterpret_cast<float4 *>(a.z + 4 * (size_t)row) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+                if (cheb_m <= 1)      // (Chebyshev: the preconditioned residual is already published in zcur)
+                    *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row) = make_float4(zz[0], zz[1], zz[2], zz[3]);
             }
             sync.barrier();
         }
@@ -607,10 +704,10 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                             float4 xa[UB], xb[UB];
 #pragma unroll
                             for (int u = 0; u < UB; ++u) {
-                                xa[u] = lsp::ld_coherent4(a.z + 4 * (size_t)cv[u].x);
-                                xb[u] = lsp::ld_coherent4(a.z + 4 * (size_t)cv[u].y);
+                                xa[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
+                                xb[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].y);
                             }
-                            zo = lsp::ld_coherent4(a.z + 4 * (size_t)row);
+                            zo = lsp::ld_coherent4(zcur + 4 * (size_t)row);
                             dp = a.diagp[row];
 #pragma unroll
                             for (int k = 0; k < K; ++k) {
@@ -641,8 +738,8 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                             float4 xa[U], xb[U];
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
-                                xa[u] = lsp::ld_coherent4(a.z + 4 * (size_t)cv[u].x);
-                                xb[u] = lsp::ld_coherent4(a.z + 4 * (size_t)cv[u].y);
+                                xa[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
+                                xb[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].y);
                             }
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
@@ -664,7 +761,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                         {
                             float4 xv[U];
 #pragma unroll
-                            for (int u = 0; u < U; ++u) xv[u] = lsp::ld_coherent4(a.z + 4 * (size_t)cv[u].x);
+                            for (int u = 0; u < U; ++u) xv[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
 #pragma unroll
                             for (int k = 0; k < K; ++k) {
                                 po[k] = P(li, k, row);
@@ -690,7 +787,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                             for (int u = 0; u < U; ++u) cv[u] = (j + u < w) ? ld_ent<KEEP>(e + (j + u) * 32) : make_int2(row, 0);
                             float4 xv[U];
 #pragma unroll
-                            for (int u = 0; u < U; ++u) xv[u] = lsp::ld_coherent4(a.z + 4 * (size_t)cv[u].x);
+                            for (int u = 0; u < U; ++u) xv[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const float wv = __int_as_float(cv[u].y);
@@ -739,6 +836,16 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 double acc2[2 * K];
 #pragma unroll
                 for (int i = 0; i < 2 * K; ++i) acc2[i] = 0.0;
+                if (cheb_m > 1) {
+                    for (int s = s_begin + warp; s < s_end; s += NW) {
+                        const int li = s - s_begin, row = s * 32 + lane;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) R(li, k, row) = fmaf(-alpha[k], Sv(li, k, row), R(li, k, row));
+                    }
+                    __syncwarp();
+                    cheb_first();
+                    cheb_steps(acc2);
+                } else
                 for (int s = s_begin + warp; s < s_end; s += NW) {
                     const int li = s - s_begin, row = s * 32 + lane;
                     const float di = Dv(li, row);
@@ -752,7 +859,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                         acc2[k] += (double)(di * r2);
                         acc2[K + k] += (double)r2;
                     }
-                    *reinterpret_cast<float4 *>(a.z + 4 * (size_t)row) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+                    *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row) = make_float4(zz[0], zz[1], zz[2], zz[3]);
                 }
                 if (prof) { const long long t1 = clock64(); tB += t1 - t0; t0 = t1; }
                 auto postB = [&](const double gn, const double rrn) {   // beta, convergence, stop decision

@@ -28,6 +28,21 @@ ORDER_MIN_V = 8192   # below this everything lives in L1/L2 anyway
 _csr_cache = {}
 
 
+class _TorchAlloc:
+    """default allocator of the assembly: one torch tensor per buffer (largesteps_b200.remesh substitutes an arena)"""
+
+    @staticmethod
+    def take(nbytes, dev):
+        return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=dev)
+
+
+_ESIZE = {torch.int64: 8, torch.int32: 4, torch.float32: 4}
+
+
+def _view(buf, dtype, n):
+    return buf[: n * _ESIZE[dtype]].view(dtype)
+
+
 def _remember_csr(M, rowptr, col, val, order=None):
     key = id(M)
 
@@ -45,16 +60,16 @@ def order_of(M):
     return None
 
 
-def morton_order(verts):
+def morton_order(verts, alloc=_TorchAlloc):
     """perm[new] = old along a Morton curve of the vertex positions (csrc/ls_order.cu); deterministic."""
     N.require_cuda(verts, "verts")
     v = verts.detach().to(torch.float32).contiguous()
     V = v.shape[0]
-    perm = torch.empty(V + 8, dtype=torch.int32, device=v.device)[:V]
+    perm = _view(alloc.take(4 * (V + 8), v.device), torch.int32, V + 8)[:V]
     with torch.cuda.device(v.device):
         nbytes = ctypes.c_size_t(0)
         N.check(N.lib().ls_order_workspace_bytes(V, ctypes.byref(nbytes)), "ls_order_workspace_bytes")
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=v.device)
+        ws = alloc.take(nbytes.value, v.device)
         N.check(N.lib().ls_order_morton(N.ptr(v), V, N.ptr(perm), N.ptr(ws), nbytes.value, N.stream_ptr(v.device)),
                 "ls_order_morton")
     return perm
@@ -88,7 +103,7 @@ def csr_of(M):
     return rowptr, col, val
 
 
-def _assemble(verts, faces, shift, scale, cotan):
+def _assemble(verts, faces, shift, scale, cotan, alloc=_TorchAlloc):
     N.require_cuda(verts, "verts")
     N.require_cuda(faces, "faces")
     if faces.device != verts.device:
@@ -108,15 +123,15 @@ def _assemble(verts, faces, shift, scale, cotan):
         st = N.stream_ptr(dev)
         nbytes = ctypes.c_size_t(0)
         N.check(lib.ls_assemble_workspace_bytes(F, V, ctypes.byref(nbytes)), "ls_assemble_workspace_bytes")
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        ws = alloc.take(nbytes.value, dev)
         nnz = ctypes.c_int64(0)
         N.check(lib.ls_assemble_count(N.ptr(faces_c), faces_c.element_size(), F, V, N.ptr(ws), nbytes.value,
                                       ctypes.byref(nnz), st), "ls_assemble_count")
         nnz = nnz.value
-        idx = torch.empty((2, nnz), dtype=torch.int64, device=dev)
-        val = torch.empty(nnz + 8, dtype=torch.float32, device=dev)[:nnz]
-        rowptr = torch.empty(V + 1 + 8, dtype=torch.int32, device=dev)[: V + 1]
-        col = torch.empty(nnz + 8, dtype=torch.int32, device=dev)[:nnz]
+        idx = _view(alloc.take(16 * nnz, dev), torch.int64, 2 * nnz).view(2, nnz)
+        val = _view(alloc.take(4 * (nnz + 8), dev), torch.float32, nnz + 8)[:nnz]
+        rowptr = _view(alloc.take(4 * (V + 1 + 8), dev), torch.int32, V + 1 + 8)[: V + 1]
+        col = _view(alloc.take(4 * (nnz + 8), dev), torch.int32, nnz + 8)[:nnz]
         # COO values and CSR values are the same array (same order): write it once
         N.check(lib.ls_assemble_fill(N.ptr(faces_c), faces_c.element_size(), N.ptr(verts_c), F, V, int(bool(cotan)),
                                      float(shift), float(scale), N.ptr(ws), nbytes.value, nnz,
@@ -126,7 +141,7 @@ def _assemble(verts, faces, shift, scale, cotan):
         warnings.simplefilter("ignore")
         M = torch.sparse_coo_tensor(idx, val, (V, V), is_coalesced=True, check_invariants=False)
     # the solver re-orders its private copy of M along a Morton curve of the positions (the public M is untouched)
-    order = morton_order(verts) if V >= ORDER_MIN_V else None
+    order = morton_order(verts, alloc) if V >= ORDER_MIN_V else None
     _remember_csr(M, rowptr, col, val, order)
     return M
 
@@ -141,11 +156,12 @@ def laplacian_cot(verts, faces):
     return _assemble(verts, faces, 0.0, 1.0, True)
 
 
-def compute_matrix(verts, faces, lambda_, alpha=None, cotan=False):
+def compute_matrix(verts, faces, lambda_, alpha=None, cotan=False, alloc=None):
     """Build the parameterization matrix (geometry.py:96-133).
 
     If alpha is defined, M = (1-alpha)*I + alpha*L, otherwise M = I + lambda_*L (lambda_ is ignored when alpha is
     given, as in the reference).  Returns a coalesced float32 torch.sparse_coo_tensor with int64 indices.
+    `alloc` (not in the reference): where the output and work buffers come from (largesteps_b200.remesh.Arena).
     """
     if alpha is None:
         shift, scale = 1.0, float(lambda_)
@@ -153,4 +169,4 @@ def compute_matrix(verts, faces, lambda_, alpha=None, cotan=False):
         if alpha < 0.0 or alpha >= 1.0:
             raise ValueError(f"Invalid value for alpha: {alpha} : it should take values between 0 (included) and 1 (excluded)")
         shift, scale = 1.0 - alpha, float(alpha)
-    return _assemble(verts, faces, shift, scale, cotan)
+    return _assemble(verts, faces, shift, scale, cotan, alloc if alloc is not None else _TorchAlloc)

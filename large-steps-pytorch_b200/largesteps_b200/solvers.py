@@ -57,7 +57,7 @@ class PCGSolver(Solver):
     """
 
     def __init__(self, M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, strict=False, reorder=True,
-                 check=True, refine=1, theta=3.0):
+                 check=True, refine=1, theta=3.0, workspace=None):
         if precond not in ("jacobi", "none"):
             raise ValueError(f"Unknown preconditioner '{precond}'.")
         rowptr, col, val = csr_of(M)
@@ -82,7 +82,12 @@ class PCGSolver(Solver):
         with torch.cuda.device(self.device):
             nbytes = ctypes.c_size_t(0)
             N.check(lib.ls_pcg_workspace_bytes(self.V, self.nnz, K_MAX, ctypes.byref(nbytes)), "ls_pcg_workspace_bytes")
-            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)   # owned by this object
+            if workspace is None:
+                self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)   # owned by this object
+            else:   # caller-provided device memory (largesteps_b200.remesh re-uses one arena across re-parameterisations)
+                if workspace.numel() < nbytes.value or workspace.data_ptr() % 256 != 0 or workspace.device != self.device:
+                    raise ValueError(f"workspace must be a 256-byte aligned uint8 tensor of >= {nbytes.value} bytes on {self.device}")
+                self._ws = workspace
             N.check(lib.ls_pcg_create(ctypes.byref(self._handle), self.V, self.nnz, N.ptr(rowptr), N.ptr(col),
                                       N.ptr(val), N.ptr(order), 1 if precond == "jacobi" else 0, K_MAX, N.ptr(self._ws),
                                       nbytes.value, N.stream_ptr(self.device)), "ls_pcg_create")
@@ -256,22 +261,30 @@ def bench_kernels(solvers, which, launches, k=3):
         N.check(N.lib().ls_pcg_bench(arr, len(solvers), k, which, launches, N.stream_ptr(dev)), "ls_pcg_bench")
 
 
+def workspace_bytes(V, nnz):
+    """Device bytes a solver handle for a (V, V) matrix with nnz entries needs (ls_pcg_workspace_bytes)."""
+    nbytes = ctypes.c_size_t(0)
+    N.check(N.lib().ls_pcg_workspace_bytes(int(V), int(nnz), K_MAX, ctypes.byref(nbytes)), "ls_pcg_workspace_bytes")
+    return nbytes.value
+
+
 class CholeskySolver(PCGSolver):
     """Drop-in for the reference CholeskySolver (solvers.py:26-39).  No factorisation happens: the system is
     solved by the device PCG from a cold start to a relative residual of 1e-7 (<= 1e-5 rel-L2 of a direct solve).
     One asynchronous kernel launch per solve (`check=False`); `.raise_for_status()` checks the last solve on demand."""
 
-    def __init__(self, M):
+    def __init__(self, M, workspace=None):
         # like cholespy's solve, the call is asynchronous; a solve that did not converge is reported at the next call
-        super().__init__(M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, check=False, refine=1)
+        super().__init__(M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, check=False, refine=1,
+                         workspace=workspace)
 
 
 class ConjugateGradientSolver(PCGSolver):
     """Drop-in for the reference ConjugateGradientSolver (solvers.py:41-126): keeps its separate forward/backward
     warm starts; uses a *relative* tolerance and an iteration cap instead of the reference's absolute 1e-5."""
 
-    def __init__(self, M):
-        super().__init__(M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=True)
+    def __init__(self, M, workspace=None):
+        super().__init__(M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=True, workspace=workspace)
 
 
 class DifferentiableSolve(Function):

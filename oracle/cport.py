@@ -39,6 +39,44 @@ def lib():
     return _lib
 
 
+def host_cpu_budget():
+    """What this process may actually use: CPUs in its affinity mask and the cgroup CPU quota (cores), if any."""
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    quota = None
+    raw = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            raw = open(path).read().strip()
+        except OSError:
+            continue
+        try:
+            if path.endswith("cpu.max"):
+                a, b = raw.split()
+                quota = None if a == "max" else float(a) / float(b)
+            else:
+                qv = float(raw)
+                per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                quota = None if qv <= 0 else qv / per
+        except Exception:
+            quota = None
+        break
+    return {"affinity_cpus": ncpu, "quota_cores": quota, "cgroup_cpu_max": raw}
+
+
+def pin_to_allowed_cores(n):
+    """Restrict this process to the first n CPUs of its affinity mask (OpenMP threads inherit it): keeps the team on a fixed
+    set of cores instead of migrating across a large shared host."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, set(cpus[:max(1, n)]))
+        return cpus[:max(1, n)]
+    except (AttributeError, OSError):
+        return None
+
+
 class CPortCG:
     """Same interface as oracle.ReferenceCG / the reference's ConjugateGradientSolver."""
 
@@ -55,32 +93,31 @@ class CPortCG:
         self.threads = lib().lsref_num_threads()
 
     def autotune_threads(self, b, probe_iters=8):
-        """Pick the OpenMP thread count that runs a few CG iterations fastest.  The default (one thread per logical CPU)
-        can be far from it: under a cgroup CPU quota 128 threads on a 16-core allowance run 500x slower than 16."""
+        """Pick the OpenMP thread count.  The boxes run under a cgroup CPU quota (see host_cpu_budget): the default of one
+        thread per logical CPU can be 500x slower than one thread per allowed core.  Candidates are therefore centred on the
+        quota (quota/2, quota, 2 quota, capped by the affinity mask) and the fastest over a few CG iterations wins."""
         import time
-        try:
-            ncpu = len(os.sched_getaffinity(0))
-        except AttributeError:
-            ncpu = os.cpu_count() or 1
-        cands = [t for t in (1, 2, 4, 8, 16, 24, 32, 48, 64, 96, 128, 192, 256) if t <= ncpu] or [1]
+        budget = host_cpu_budget()
+        ncpu = budget["affinity_cpus"]
+        q = budget["quota_cores"]
+        if q:
+            cands = sorted({max(1, min(ncpu, int(round(c)))) for c in (q / 2, q, 2 * q)})
+        else:   # no visible quota (it may still exist one level up): scan powers of two
+            cands = [t for t in (4, 8, 16, 32, 64, 128, 256) if t <= ncpu] or [ncpu]
         save = (self.guess_fwd, self.guess_bwd)
-        best_t, best_dt, worse = cands[0], float("inf"), 0
+        best_t, best_dt = cands[0], float("inf")
         for t in cands:
             lib().lsref_set_num_threads(t)
             self.guess_fwd = None
             self.solve(b, maxit=1)                     # thread pool start-up at this size
             dt = float("inf")
-            for _ in range(2):                         # best of two: shared hosts are noisy
+            for _ in range(3):                         # best of three: shared hosts are noisy
                 self.guess_fwd = None
                 t0 = time.perf_counter()
                 self.solve(b, maxit=probe_iters)
                 dt = min(dt, time.perf_counter() - t0)
             if dt < best_dt:
-                best_t, best_dt, worse = t, dt, 0
-            else:
-                worse += 1
-                if worse >= 2:
-                    break
+                best_t, best_dt = t, dt
         lib().lsref_set_num_threads(best_t)
         self.threads = best_t
         self.guess_fwd, self.guess_bwd = save

@@ -74,3 +74,50 @@ def test_tutorial_shaped_loop_tracks_cpu_oracle():
             uo = oo.step(uo, go.astype(np.float32))
             assert rel_l2(u.detach().cpu().numpy(), uo) < 1e-4, step
     assert losses[-1] < 0.05 * losses[0]
+
+
+def test_config5_standin_2000_steps_at_52k(bunny_mesh):
+    """BASELINE config 5 stand-in at paper scale: bunny subdivided x2 (V = 52,786), cotangent lambda = 19, 2000 steps of
+    from_differential -> loss -> backward -> AdamUniform.  Every 100 steps the hot path is checked against the oracle ON
+    THE STATE THE LOOP HAS REACHED: forward solve of the current u and backward solve of the current gradient vs the fp64
+    direct solve, and the fused AdamUniform step vs the oracle step from the same moments."""
+    v, f = bunny_mesh
+    v, f = workloads.subdivide(*workloads.subdivide(v, f))
+    v = v.astype(np.float32)
+    V = len(v)
+    lam = 19.0
+    tv, tf = to_dev(v, f)
+    M = compute_matrix(tv, tf, lam, cotan=True)
+    r, c, val, _ = oracle.compute_matrix(v, f, lam, cotan=True)
+    ds = oracle.DirectSolver(r, c, val, V)
+    target = (v * (1.0 + 0.2 * np.sin(8 * v[:, :1]) * np.cos(6 * v[:, 1:2]))).astype(np.float32)
+    tgt = torch.from_numpy(target).to(DEV)
+    u = to_differential(M, tv).clone().requires_grad_(True)
+    opt = AdamUniform([u], lr=0.01)
+    losses, worst = [], 0.0
+    for step in range(2000):
+        x = from_differential(M, u, "Cholesky")
+        loss = ((x - tgt) ** 2).mean()
+        opt.zero_grad()
+        loss.backward()
+        if step % 100 == 0:
+            un = u.detach().cpu().numpy()
+            e_f = rel_l2(x.detach().cpu().numpy(), ds.solve(un))
+            gx = (2.0 * (x.detach() - tgt) / (3 * V)).cpu().numpy()
+            e_b = rel_l2(u.grad.cpu().numpy(), ds.solve(gx))
+            st = opt.state[u] if len(opt.state[u]) else None
+            oo = oracle.AdamUniformOracle((V, 3), lr=0.01)
+            if st is not None:
+                oo.g1, oo.g2, oo.step_count = st["g1"].cpu().numpy().copy(), st["g2"].cpu().numpy().copy(), st["step"]
+            want = oo.step(un.copy(), u.grad.cpu().numpy())
+            opt.step()
+            e_a = float(np.abs(u.detach().cpu().numpy() - want).max())
+            worst = max(worst, e_f, e_b)
+            assert e_f < 1e-5 and e_b < 1e-5, (step, e_f, e_b)
+            assert e_a < 2e-6 * max(1.0, float(np.abs(want).max())), (step, e_a)
+        else:
+            opt.step()
+        losses.append(float(loss.detach()) if step % 50 == 0 else None)
+    ls = [l for l in losses if l is not None]
+    print(f"52.8K loop: loss {ls[0]:.3e} -> {ls[-1]:.3e}, worst solve rel-L2 along the trajectory {worst:.2e}")
+    assert ls[-1] < 0.05 * ls[0]
