@@ -94,7 +94,8 @@ int ls_spmm_csr_f32(int64_t V, const int32_t *rowptr, const int32_t *col, const 
  *       streaming layout (re-ordered by perm_new2old when given; b/x/x0 of ls_pcg_solve stay in the caller's
  *       numbering), extracts the Jacobi diagonal, balances the row partition, plans the SpMM blocks.
  *       The caller keeps `workspace` alive until ls_pcg_destroy.  Synchronises `stream`.
- *       precond: 0 = none, 1 = Jacobi.   k_max in [1,4].
+ *       precond: 0 = none, 1 = Jacobi, 2 = Chebyshev polynomial of degree 3 in D^-1 M on top of Jacobi (spectrum bounds from a
+ *       Gershgorin row scan; ~3x fewer CG iterations and reductions for ~1.3x the SpMVs).   k_max in [1,4].
  *       The workspace size depends on (V, nnz, k_max) only -- never on the environment.
  *   ls_pcg_solve:  b, x: (V,k) float32 row-major contiguous (ld = k); x0 = NULL for a cold start (x0 may alias x).
  *       rtol: stop when ||r_j||_2 <= rtol * ||b_j||_2 for every column j (columns freeze independently, which

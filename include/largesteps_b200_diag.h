@@ -1,6 +1,6 @@
 /*
  * largesteps_b200_diag.h -- diagnostics and timing harnesses of libls_b200.so.  NOT part of the drop-in boundary
- * (include/largesteps_b200.h): nothing on the product path calls these; bench.py and profiles/*.py do.
+ * (include/largesteps_b200.h): nothing on the product path calls these; bench.py and the scripts under profiles/ do.
  */
 #ifndef LARGESTEPS_B200_DIAG_H
 #define LARGESTEPS_B200_DIAG_H
@@ -16,7 +16,8 @@ extern "C" {
 int ls_pcg_bench_spmm(void *handle, int k, int launches, void *stream);
 /* timing harness for the iteration kernels, launched back-to-back from C (a Python-level loop is launch-bound):
  *   `launches` launches rotating over `n_handles` handles (use enough handles that matrix+vectors exceed L2 for an
- *   HBM-cold number, one handle for the L2-resident number).  which: 0 SpMM+dot, 1 update, 2 p-update, 3 all three. */
+ *   HBM-cold number, one handle for the L2-resident number).  which: 0 SpMM+dot, 1 update, 2 p-update, 3 all three,
+ *   4 SpMM without the dot-product epilogue (the plain SpMV of BASELINE's metric). */
 int ls_pcg_bench(void **handles, int n_handles, int k, int which, int launches, void *stream);
 /* with LS_PCG_PROFILE set in the environment the persistent kernel's CTA 0 accumulates SM-clock cycles per phase of
  * the last solve.  Fused solver: out8 = [phase A (SpMV + x/p/s update), all-reduce of p.s, phase B (r, z), all-reduce of

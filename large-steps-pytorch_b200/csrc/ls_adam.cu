@@ -2,8 +2,10 @@
 // + a max reduction per parameter): two streaming passes over (param, grad, g1, g2).
 //   pass 1: g1 = b1 g1 + (1-b1) g ; g2 = b2 g2 + (1-b2) g^2 ; gmax = max(g2)        (optimize.py:35-36)
 //   pass 2: p -= lr * (g1/c1) / (1e-8 + sqrt(gmax/c2))                                 (optimize.py:37-41)
-// max(sqrt(g2/c2)) == sqrt(max(g2)/c2) exactly in fp32 (both maps are monotone), so the scalar normaliser of
-// optimize.py:40 is reproduced exactly; the max itself is order independent (deterministic).
+// max(sqrt(g2/c2)) == sqrt(max(g2)/c2) in fp32 (both maps are monotone), so the scalar normaliser of optimize.py:40 is
+// reproduced to the last bit or one ulp (torch divides by a Python scalar as multiply-by-reciprocal; here it is a division);
+// the max itself is order independent (deterministic).  A NaN in the moments makes the normaliser NaN, as torch's max() does:
+// divergence poisons every parameter and is visible, instead of being dropped by fmaxf.
 #include "ls_common.cuh"
 
 namespace {
@@ -13,6 +15,7 @@ __global__ void __launch_bounds__(AT) k_adam_moments(const float *__restrict__ g
                                                      float *__restrict__ g2, int64_t n, float b1, float b2,
                                                      float omb1, float omb2, unsigned int *__restrict__ gmax_bits) {
     float m = 0.f;
+    bool nan_seen = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float g = grad[i];
         // g1.mul_(b1).add_(grad, alpha=1-b1): the in-place mul rounds, torch's CUDA add(alpha) contracts to an fma
@@ -21,7 +24,9 @@ __global__ void __launch_bounds__(AT) k_adam_moments(const float *__restrict__ g
         g1[i] = a;
         g2[i] = b;
         m = fmaxf(m, b);
+        nan_seen |= (b != b);
     }
+    if (__any_sync(0xffffffffu, nan_seen) && (threadIdx.x & 31) == 0) atomicOr(gmax_bits + 1, 1u);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     __shared__ float wm[AT / 32];
@@ -38,7 +43,7 @@ __global__ void __launch_bounds__(AT) k_adam_moments(const float *__restrict__ g
 __global__ void __launch_bounds__(AT) k_adam_apply(float *__restrict__ param, const float *__restrict__ g1, int64_t n,
                                                    float lr, float c1, float c2,
                                                    const unsigned int *__restrict__ gmax_bits) {
-    const float gmax = __uint_as_float(*gmax_bits);
+    const float gmax = gmax_bits[1] ? __int_as_float(0x7fc00000) : __uint_as_float(*gmax_bits);
     const float denom = __fadd_rn(1e-8f, __fsqrt_rn(__fdiv_rn(gmax, c2)));   // 1e-8 + m2.sqrt().max()
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float m1 = __fdiv_rn(g1[i], c1);

@@ -99,15 +99,18 @@ __global__ void k_sort_buckets(int64_t nb, const int *__restrict__ start, int *_
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     int s = start[b], e = start[b + 1];
-    for (int a = s + 1; a < e; ++a) {
-        int v = perm[a];
-        int j = a - 1;
-        while (j >= s && perm[j] > v) {
-            perm[j + 1] = perm[j];
-            --j;
+    // shell sort (a cell that catches 1e5 coincident or outlier-squeezed vertices must not cost 1e10 operations)
+    const int n = e - s;
+    for (int gap = n >> 1; gap > 0; gap >>= 1)
+        for (int a = s + gap; a < e; ++a) {
+            int v = perm[a];
+            int j = a - gap;
+            while (j >= s && perm[j] > v) {
+                perm[j + gap] = perm[j];
+                j -= gap;
+            }
+            perm[j + gap] = v;
         }
-        perm[j + 1] = v;
-    }
 }
 
 struct OrderWs {

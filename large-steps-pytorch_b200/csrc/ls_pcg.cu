@@ -101,8 +101,12 @@ struct PcgHandle {
     size_t persist_smem;
     // fused two-synchronisation solver (ls_pcg_fused.cuh): the default; one configuration for K = 3 (k = 1..3) and one for K = 4
     float *pv;               // owner copy of p, k_max planes
+    float *z2, *cy, *cd;     // Chebyshev preconditioner: second published row buffer, iterate and direction planes
+    int cheb_m;              // 0 / 1: Jacobi only; m >= 2: polynomial of degree m - 1 (precond = 2)
+    float cheb_c0, cheb_c1[8], cheb_c2[8];
+    float *gersh;            // [1] max_i sum_j |a_ij| / a_ii
     struct FusedCfg {
-        int on, grid, res, nw, sync, cluster, nsl_max, pat;
+        int on, grid, res, nw, sync, cluster, nsl_max, pat, dp;
         size_t smem;
         const void *fn, *fn_prof;
     } fused[2];
@@ -110,6 +114,7 @@ struct PcgHandle {
     int refine;              // max restarts from the true residual per solve
     float theta;
     int sell_tma;            // stand-alone SpMM: TMA-staged variant (0 = register-prefetch kernel)
+    int sell_pf;             // ... halo (rows) of its bulk L2 prefetch of the gathered vector, 0 = off
     // graphs, one per K
     cudaGraphExec_t graph[KMAX + 1];
     cudaStream_t cap_stream;
@@ -144,6 +149,9 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
     size_t o_p = c.take((size_t)Vp * 4 * 4);            // p: rows of PW <= 4 floats
     size_t o_Ap = c.take((size_t)Vp * 4 * k_max);
     size_t o_pown = c.take((size_t)Vp * 4 * k_max);
+    size_t o_z2 = c.take((size_t)Vp * 4 * 4);
+    size_t o_cy = c.take((size_t)Vp * 4 * k_max);
+    size_t o_cd = c.take((size_t)Vp * 4 * k_max);
     size_t o_part = c.take((size_t)(grid_cap + 1) * 4);
     size_t o_desc = c.take((size_t)grid_cap * lsk::SPMM_BMAX * sizeof(int4));
     size_t o_dcnt = c.take((size_t)grid_cap * 4);
@@ -169,6 +177,7 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
     size_t o_pcol = c.take((size_t)sell_cap * 4);         // sell_cap / 2 pairs of 8 bytes
     size_t o_diagp = c.take((size_t)Vp * 4);
     size_t o_patmm = c.take(64);
+    size_t o_gersh = c.take(64);
     if (h && base) {
         h->Vp = Vp;
         h->rowptr = (int *)(base + o_rp);
@@ -180,6 +189,9 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
         h->p = (float *)(base + o_p);
         h->Ap = (float *)(base + o_Ap);
         h->pv = (float *)(base + o_pown);
+        h->z2 = (float *)(base + o_z2);
+        h->cy = (float *)(base + o_cy);
+        h->cd = (float *)(base + o_cd);
         h->part = (int *)(base + o_part);
         h->desc = (int4 *)(base + o_desc);
         h->desc_cnt = (int *)(base + o_dcnt);
@@ -205,6 +217,7 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
         h->pcol = (int2 *)(base + o_pcol);
         h->diagp = (float *)(base + o_diagp);
         h->patmm = (unsigned int *)(base + o_patmm);
+        h->gersh = (float *)(base + o_gersh);
         h->pat_cap = sell_cap / 2;
     }
     return c.off;
@@ -244,6 +257,26 @@ __global__ void k_dinv(int64_t V, int64_t Vp, const int *__restrict__ rowptr, co
     }
     if (!found || !(d > 0.f)) atomicOr(flags, 2);
     dinv[i] = precond ? (1.0f / d) : 1.0f;
+}
+
+// Gershgorin bound of lambda_max(D^-1 A): max_i sum_j |a_ij| / a_ii   (positive floats order like their bit patterns)
+__global__ void k_gershgorin(int64_t V, const int *__restrict__ rowptr, const int *__restrict__ col, const float *__restrict__ val,
+                             float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float g = 0.f;
+    if (i < V) {
+        float d = 0.f, sabs = 0.f;
+        for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
+            const float a = val[j];
+            sabs += fabsf(a);
+            if (col[j] == (int)i) d += a;
+        }
+        g = d > 0.f ? sabs / d : 0.f;
+    }
+    g = fmaxf(g, 0.f);
+    unsigned int b = __float_as_uint(g);
+    b = __reduce_max_sync(0xffffffffu, b);
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(reinterpret_cast<unsigned int *>(out), b);
 }
 
 // ---- permuted copy  A' = P A P^T  (perm[new] = old) ------------------------------------------------
@@ -650,16 +683,16 @@ lsk::SpmmArgs spmm_args(PcgHandle *h, int K, bool with_done) {
 
 // TMA-staged SELL SpMM (ls_sell_kernel.cuh): per-warp shared-memory rings fed by cp.async.bulk, launched with programmatic
 // stream serialisation so that its matrix prefetch overlaps the tail of the previous kernel in the stream.
-template <int K, int NW, int DEPTH>
+template <int K, bool DOT, int NW, int DEPTH, int MINB>
 int launch_sell_tma_t(PcgHandle *h, const lsk::SellArgs &a, cudaStream_t s) {
     static bool prepared = false;
     const size_t smem = lsk::sell_tma_smem_bytes(NW, DEPTH);
     if (!prepared) {
-        LS_CUDA_TRY(cudaFuncSetAttribute(lsk::spmm_sell_tma_kernel<K, true, NW, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LS_CUDA_TRY(cudaFuncSetAttribute(lsk::spmm_sell_tma_kernel<K, DOT, NW, DEPTH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prepared = true;
     }
     cudaLaunchConfig_t lc = {};
-    int g = h->nslices < h->sm_count ? h->nslices : h->sm_count;
+    int g = h->nslices < h->sm_count * MINB ? h->nslices : h->sm_count * MINB;
     lc.gridDim = dim3(g < 1 ? 1 : g);
     lc.blockDim = dim3(NW * 32);
     lc.dynamicSmemBytes = smem;
@@ -669,21 +702,24 @@ int launch_sell_tma_t(PcgHandle *h, const lsk::SellArgs &a, cudaStream_t s) {
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
     lc.numAttrs = (h->sell_tma >= 10) ? 0 : 1;   // LS_SELL_TMA >= 10: same kernels without PDL (A/B)
-    LS_CUDA_TRY(cudaLaunchKernelEx(&lc, lsk::spmm_sell_tma_kernel<K, true, NW, DEPTH>, a));
+    LS_CUDA_TRY(cudaLaunchKernelEx(&lc, lsk::spmm_sell_tma_kernel<K, DOT, NW, DEPTH, MINB>, a));
     g_ls_launches.fetch_add(1, std::memory_order_relaxed);
     return LS_OK;
 }
-template <int K>
+template <int K, bool DOT = true>
 int launch_sell_tma(PcgHandle *h, const lsk::SellArgs &a, cudaStream_t s) {
     if constexpr (K == 3) {
         switch (h->sell_tma % 10) {
-            case 2: return launch_sell_tma_t<K, 24, 4>(h, a, s);
-            case 3: return launch_sell_tma_t<K, 32, 2>(h, a, s);
-            case 4: return launch_sell_tma_t<K, 16, 6>(h, a, s);
+            case 2: return launch_sell_tma_t<K, DOT, 24, 4, 1>(h, a, s);
+            case 4: return launch_sell_tma_t<K, DOT, 16, 6, 1>(h, a, s);
+            case 5: return launch_sell_tma_t<K, DOT, 16, 3, 2>(h, a, s);   // two CTAs per SM: the next launch's prefetch overlaps this one's tail
+            case 6: return launch_sell_tma_t<K, DOT, 24, 2, 2>(h, a, s);
+            case 7: return launch_sell_tma_t<K, DOT, 16, 2, 2>(h, a, s);   // 2 x 66 KB of rings: ~95 KB of L1 left for the gathers
             default: break;
         }
     }
-    return launch_sell_tma_t<K, 32, 3>(h, a, s);
+    if (h->sell_tma % 10 == 1) return launch_sell_tma_t<K, DOT, 32, 3, 1>(h, a, s);
+    return launch_sell_tma_t<K, DOT, 32, 2, 1>(h, a, s);
 }
 
 template <int K>
@@ -701,6 +737,7 @@ int launch_spmm(PcgHandle *h, bool with_done, cudaStream_t s) {
         a.partials = h->part_spmm;
         a.ticket = h->tickets + 0;
         a.dot_out = h->ctrl->pAp;
+        a.pf_halo = h->sell_pf;
         if (h->sell_tma) return launch_sell_tma<K>(h, a, s);
         lsk::spmm_sell_kernel<K, true><<<h->sell_grid, lsk::SELL_THREADS, 0, s>>>(a);
         LS_LAUNCH_CHECK();
@@ -846,11 +883,22 @@ int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int max
 
 // ---- fused two-synchronisation solver (ls_pcg_fused.cuh) ------------------------------------------------------------
 // instantiation table: (K, RES, NW, PAT, SYNC, PROF) -> kernel, or NULL when that combination is not built
-template <int K, int RES, int NW, bool PAT, int SYNC, bool PROF>
-const void *ffn() { return (const void *)lsf::pcg_fused_kernel<K, RES, NW, PAT, SYNC, PROF>; }
+template <int K, int RES, int NW, bool PAT, int SYNC, bool PROF, bool CHEB = false>
+const void *ffn() { return (const void *)lsf::pcg_fused_kernel<K, RES, NW, PAT, SYNC, PROF, CHEB>; }
 
-const void *fused_fn(int K, int res, int nw, int pat, int sync, int prof) {
+const void *fused_fn(int K, int res, int nw, int pat, int sync, int prof, int cheb = 0) {
     constexpr int W = lsp::PWARPS, WS = lsp::PT_SMALL / 32;
+    if (cheb) {   // Chebyshev preconditioner instantiations
+        if (K != 3 || prof) return nullptr;
+        if (sync == 0 && nw == W) {
+            if (res == 0) return pat ? ffn<3, 0, W, true, 0, false, true>() : ffn<3, 0, W, false, 0, false, true>();
+            if (res == 1) return pat ? ffn<3, 1, W, true, 0, false, true>() : ffn<3, 1, W, false, 0, false, true>();
+            if (res == 2) return pat ? ffn<3, 2, W, true, 0, false, true>() : ffn<3, 2, W, false, 0, false, true>();
+        }
+        if (sync == 0 && nw == WS && res == 2) return pat ? ffn<3, 2, WS, true, 0, false, true>() : ffn<3, 2, WS, false, 0, false, true>();
+        if (sync == 1 && nw == W && res == 2) return pat ? ffn<3, 2, W, true, 1, false, true>() : ffn<3, 2, W, false, 1, false, true>();
+        return nullptr;
+    }
     if (K == 3 && !prof) {
         if (sync == 0 && nw == W) {
             if (res == 0) return pat ? ffn<3, 0, W, true, 0, false>() : ffn<3, 0, W, false, 0, false>();
@@ -859,11 +907,13 @@ const void *fused_fn(int K, int res, int nw, int pat, int sync, int prof) {
         }
         if (sync == 0 && nw == WS && res == 2) return pat ? ffn<3, 2, WS, true, 0, false>() : ffn<3, 2, WS, false, 0, false>();
         if (sync == 1 && nw == W && res == 2) return pat ? ffn<3, 2, W, true, 1, false>() : ffn<3, 2, W, false, 1, false>();
+        if (sync == 1 && nw == W && res == 3) return pat ? ffn<3, 3, W, true, 1, false>() : ffn<3, 3, W, false, 1, false>();
     }
     if (K == 3 && prof && nw == W) {
         if (sync == 0 && res == 1) return pat ? ffn<3, 1, W, true, 0, true>() : ffn<3, 1, W, false, 0, true>();
         if (sync == 0 && res == 2) return pat ? ffn<3, 2, W, true, 0, true>() : ffn<3, 2, W, false, 0, true>();
         if (sync == 1 && res == 2) return pat ? ffn<3, 2, W, true, 1, true>() : ffn<3, 2, W, false, 1, true>();
+        if (sync == 1 && res == 3) return pat ? ffn<3, 3, W, true, 1, true>() : ffn<3, 3, W, false, 1, true>();
     }
     if (K == 4 && !prof && !pat && nw == W) {
         if (sync == 0 && res == 0) return ffn<4, 0, W, false, 0, false>();
@@ -888,29 +938,33 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
     if (algo && (algo[0] == 'c' || algo[0] == 'C')) return LS_OK;          // A/B: round-1 three-synchronisation kernel
     const char *mode = getenv("LS_PCG_MODE");
     if (mode && (mode[0] == 'g' || mode[0] == 'G')) return LS_OK;
+    const int cheb = (K == 3 && h->cheb_m > 1) ? 1 : 0;
     const int pat = (K == 3 && h->pat_on) ? 1 : 0;
     const int W = lsp::PWARPS;
-    auto cap_slices = [&](int res) {   // slices per CTA that fit in shared memory at this residency level
+    auto cap_slices = [&](int res, int dp) {   // slices per CTA that fit in shared memory at this residency level
         if (res == 0) return 1 << 30;
         int n = 0;
-        while (lsf::fused_smem_bytes(K, res, n + 1) <= (size_t)di.max_smem_optin) ++n;
+        while (lsf::fused_smem_bytes(K, res, n + 1, dp, cheb) <= (size_t)di.max_smem_optin) ++n;
         return n;
     };
-    const int cap2 = cap_slices(2), cap1 = cap_slices(1);
+    const int cap3 = cap_slices(3, pat), cap2 = cap_slices(2, 0), cap1 = cap_slices(1, 0);
     const int want_cluster = env_int("LS_PCG_CLUSTER", -1);   // -1 auto, 0 never, N force cluster size N
     const int force_res = env_int("LS_PCG_RES", -1);
-    // ---- one cluster?
+    // ---- one CTA (everything, including the gathered vector, in shared memory) or, on request, one cluster
+    // A cluster of 16 was measured slower than the cooperative grid for mid-size meshes (bunny x2: 1.81 vs 0.72 ms): 16 SMs
+    // give 16 x ~28 B/clk of L2 bandwidth and cluster.sync flushes L1 each time, so it is opt-in (LS_PCG_CLUSTER=N).
     int cs = 0;
     if (want_cluster != 0) {
         if (h->nslices <= 4 * W) cs = 1;
-        else if ((h->nslices + 15) / 16 <= cap2) cs = 16;
         if (want_cluster > 0) cs = want_cluster;
         if (cs > 0 && (h->nslices + cs - 1) / cs > cap2) cs = 0;
     }
     if (cs > 0) {
-        const void *fn = fused_fn(K, 2, W, pat, 1, 0);
         const int nsl_max = (h->nslices + cs - 1) / cs;
-        const size_t smem = lsf::fused_smem_bytes(K, 2, nsl_max);
+        int res = (cs == 1 && K == 3 && h->cheb_m <= 1 && nsl_max <= cap3 && !(force_res >= 0 && force_res < 3)) ? 3 : 2;
+        const int dp = (pat && nsl_max <= cap_slices(res, 1)) ? 1 : 0;
+        const void *fn = fused_fn(K, res, W, pat, 1, 0, cheb);
+        const size_t smem = lsf::fused_smem_bytes(K, res, nsl_max, dp, cheb);
         bool ok = fn != nullptr;
         if (ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin) != cudaSuccess) ok = false;
         if (ok && cs > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = false;
@@ -930,8 +984,8 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
             if (cudaOccupancyMaxActiveClusters(&ncl, fn, &lc) != cudaSuccess || ncl < 1) ok = false;
         }
         if (ok) {
-            c->on = 1; c->grid = cs; c->res = 2; c->nw = W; c->sync = 1; c->cluster = cs; c->nsl_max = nsl_max; c->pat = pat;
-            c->smem = smem; c->fn = fn; c->fn_prof = fused_fn(K, 2, W, pat, 1, 1);
+            c->on = 1; c->grid = cs; c->res = res; c->nw = W; c->sync = 1; c->cluster = cs; c->nsl_max = nsl_max; c->pat = pat; c->dp = dp;
+            c->smem = smem; c->fn = fn; c->fn_prof = cheb ? nullptr : fused_fn(K, res, W, pat, 1, 1);
             if (c->fn_prof) {
                 cudaFuncSetAttribute(c->fn_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
                 if (cs > 8) cudaFuncSetAttribute(c->fn_prof, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -956,9 +1010,10 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
     int nw = W;
     const char *et = getenv("LS_PCG_SMALLCTA");
     if (K == 3 && res == 2 && nsl_max <= 16 && !(et && et[0] == '0')) nw = lsp::PT_SMALL / 32;
-    const void *fn = fused_fn(K, res, nw, pat, 0, 0);
+    const void *fn = fused_fn(K, res, nw, pat, 0, 0, cheb);
     if (!fn) return LS_OK;
-    const size_t smem = lsf::fused_smem_bytes(K, res, nsl_max);
+    const int dp = (pat && res >= 1 && nsl_max <= cap_slices(res, 1)) ? 1 : 0;
+    const size_t smem = lsf::fused_smem_bytes(K, res, nsl_max, dp, cheb);
     // the attribute is per function and device, shared by every handle: always the device maximum, never a per-handle size
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin) != cudaSuccess) {
         cudaGetLastError();
@@ -969,8 +1024,8 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
         cudaGetLastError();
         return LS_OK;
     }
-    c->on = 1; c->grid = g; c->res = res; c->nw = nw; c->sync = 0; c->cluster = 0; c->nsl_max = nsl_max; c->pat = pat;
-    c->smem = smem; c->fn = fn; c->fn_prof = fused_fn(K, res, nw, pat, 0, 1);
+    c->on = 1; c->grid = g; c->res = res; c->nw = nw; c->sync = 0; c->cluster = 0; c->nsl_max = nsl_max; c->pat = pat; c->dp = dp;
+    c->smem = smem; c->fn = fn; c->fn_prof = cheb ? nullptr : fused_fn(K, res, nw, pat, 0, 1);
     if (c->fn_prof) cudaFuncSetAttribute(c->fn_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
     cudaGetLastError();
     return LS_OK;
@@ -997,6 +1052,16 @@ int solve_fused(PcgHandle *h, const float *b, float *x, const float *x0, int k, 
     a.r = h->r;
     a.s = h->Ap;
     a.z = h->p;
+    a.z2 = h->z2;
+    a.cy = h->cy;
+    a.cd = h->cd;
+    a.dp_smem = c.dp;
+    a.cheb_m = (k == 4) ? 0 : h->cheb_m;     // (the K = 4 instantiations carry the Jacobi preconditioner only)
+    a.cheb_c0 = h->cheb_c0;
+    for (int j = 0; j < 8; ++j) {
+        a.cheb_c1[j] = h->cheb_c1[j];
+        a.cheb_c2[j] = h->cheb_c2[j];
+    }
     a.b = b;
     a.out = x;
     a.x0 = x0;
@@ -1143,7 +1208,7 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
     *handle_out = nullptr;
     LS_REQUIRE(V > 0 && nnz > 0 && V < (int64_t)0x7ffffff0 && nnz < (int64_t)0x7ffffff0, "size out of range");
     LS_REQUIRE(k_max >= 1 && k_max <= KMAX, "k_max must be in [1,4]");
-    LS_REQUIRE(precond == 0 || precond == 1, "precond must be 0 (none) or 1 (Jacobi)");
+    LS_REQUIRE(precond >= 0 && precond <= 2, "precond must be 0 (none), 1 (Jacobi) or 2 (Chebyshev polynomial over Jacobi)");
     LS_REQUIRE(rowptr && col && val, "NULL CSR pointer");
     LS_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 255) == 0, "workspace NULL or not 256-byte aligned");
     LsDevInfo di;
@@ -1165,7 +1230,8 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
     h->sm_count = di.sm_count;
     h->max_smem_optin = di.max_smem_optin;
     h->refine = env_int("LS_PCG_REFINE", 1);
-    h->sell_tma = env_int("LS_SELL_TMA", 1);
+    h->sell_tma = env_int("LS_SELL_TMA", 3);   // 32 warps x 2 slots of 2 KB: measured best (profiles/r02_sell_tma_variants.jsonl)
+    h->sell_pf = env_int("LS_SELL_PF", 1024);
     h->theta = 3.0f;
     h->ws_bytes = need;
     carve_handle(h, (char *)workspace, V, nnz, k_max, GRID_CAP);
@@ -1298,6 +1364,14 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
         TRY_OR_FAIL(cudaMemcpyAsync(hmm, h->patmm, sizeof(hmm), cudaMemcpyDeviceToHost, stream));
     }
 
+    float hgersh = 0.f;
+    if (precond == 2) {
+        TRY_OR_FAIL(cudaMemsetAsync(h->gersh, 0, 64, stream));
+        k_gershgorin<<<(unsigned)((V + 255) / 256), 256, 0, stream>>>(V, h->rowptr, h->col, h->val, h->gersh);
+        g_ls_launches.fetch_add(1);
+        TRY_OR_FAIL(cudaGetLastError());
+        TRY_OR_FAIL(cudaMemcpyAsync(&hgersh, h->gersh, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    }
     int hflags2[2] = {0, 0};
     int sell_total = 0;
     TRY_OR_FAIL(cudaMemcpyAsync(hflags2, h->flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -1398,6 +1472,25 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
             }
         }
     }
+    h->cheb_m = 0;
+    if (precond == 2 && hgersh > 0.f) {
+        // Chebyshev semi-iteration for D^-1 A on [b/30, b], b = 1.02 x the Gershgorin bound: theta, delta, sigma = theta/delta,
+        // rho_0 = 1/sigma;  d_0 = g/theta;  rho_j = 1/(2 sigma - rho_{j-1});  d_j = rho_j rho_{j-1} d_{j-1} + 2 rho_j/delta (g - B y_j)
+        int m = env_int("LS_PCG_CHEB_M", 4);
+        if (m < 2) m = 2;
+        if (m > 8) m = 8;
+        const double b = 1.02 * (double)hgersh, a = b / 30.0;
+        const double th = 0.5 * (b + a), de = 0.5 * (b - a), sg = th / de;
+        double rho = 1.0 / sg;
+        h->cheb_c0 = (float)(1.0 / th);
+        for (int j = 1; j < m; ++j) {
+            const double rn = 1.0 / (2.0 * sg - rho);
+            h->cheb_c1[j - 1] = (float)(rn * rho);
+            h->cheb_c2[j - 1] = (float)(2.0 * rn / de);
+            rho = rn;
+        }
+        h->cheb_m = m;
+    }
     rc = configure_fused(h, di, 3, &h->fused[0]);
     if (rc) return fail(rc);
     if (k_max >= 4) {
@@ -1490,6 +1583,26 @@ int bench_one(PcgHandle *h, int which, cudaStream_t stream) {
     VecArgs va = vec_args(h, 1);
     va.bench = 1;
     if (which == 0 || which == 3) rc = launch_spmm<K>(h, false, stream);
+    if (which == 4) {   // pure y = A p, no dot-product epilogue (the SpMV of BASELINE's metric)
+        if constexpr (K == 3) {
+            if (h->sell_on && h->sell_tma) {
+                lsk::SellArgs a{};
+                a.V = (int)h->V;
+                a.nslices = h->nslices;
+                a.soff = h->soff;
+                a.ent = h->ent;
+                a.p = h->p;
+                a.y = h->Ap;
+                a.ldy = h->Vp;
+                a.pf_halo = h->sell_pf;
+                rc = launch_sell_tma<3, false>(h, a, stream);
+            } else {
+                rc = launch_spmm<K>(h, false, stream);
+            }
+        } else {
+            rc = launch_spmm<K>(h, false, stream);
+        }
+    }
     if (rc) return rc;
     if (which == 1 || which == 3) {
         k_update_cs<K><<<h->vec_grid, VEC_THREADS, 0, stream>>>(va);
@@ -1506,7 +1619,7 @@ int bench_one(PcgHandle *h, int which, cudaStream_t stream) {
 extern "C" int ls_pcg_bench(void **handles, int n_handles, int k, int which, int launches, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LS_REQUIRE(handles != nullptr && n_handles >= 1, "no handles");
-    LS_REQUIRE(which >= 0 && which <= 3, "which: 0 SpMM, 1 update, 2 p-update, 3 one full iteration");
+    LS_REQUIRE(which >= 0 && which <= 4, "which: 0 SpMM+dot, 1 update, 2 p-update, 3 one full iteration, 4 SpMM without the dot epilogue");
     for (int i = 0; i < n_handles; ++i) {
         PcgHandle *h = (PcgHandle *)handles[i];
         LS_REQUIRE(h != nullptr, "NULL handle");

@@ -55,6 +55,7 @@ struct FusedArgs {
     float *z;               // published rows of 4 floats
     float *z2;              // second row buffer (Chebyshev steps ping-pong between the two)
     float *cy, *cd;         // Chebyshev iterate and direction, K planes each (owner-only)
+    int dp_smem;            // pattern copy: corrected diagonal kept in shared memory (when it fits)
     int cheb_m;             // polynomial degree + 1 (<= 1: plain Jacobi);  z = q(D^-1 A) D^-1 r with m - 1 extra SpMVs
     float cheb_c0;          // 1 / theta
     float cheb_c1[8], cheb_c2[8];
@@ -78,7 +79,7 @@ struct Scal {
     double gam[4], bb[4], rr[4];
     float alpha[4], beta[4];
     int conv[4];
-    int it, status, stop, restarts;
+    int it, status, stop, restarts, checks;
     int e_dl[4];
     int e_grr[8];
     int skipA[4], skipB[8];
@@ -280,12 +281,16 @@ __device__ __forceinline__ int2 ld_ent(const int2 *p) {
 constexpr size_t FUSED_SMEM_HDR = 4096 + 1024;   // reduction scratch + scalars, then the cluster exchange area
 __host__ __device__ inline size_t fused_off_bytes(int nsl_max) { return ((size_t)(2 * (nsl_max + 1)) * 4 + 127) / 128 * 128; }
 
-inline size_t fused_smem_bytes(int K, int res, int nsl_max) {
-    const size_t per_slice = 32u * 4u * (res == 0 ? 0 : (res == 1 ? (2 * K + 1) : (4 * K + 1)));
-    return FUSED_SMEM_HDR + 2 * NVMAX * 16 * 8 + fused_off_bytes(nsl_max) + (size_t)nsl_max * per_slice;
+// floats per row kept in shared memory: RES 1: r, s, D^-1;  RES 2: + x, p;  RES 3 (single CTA): + the z rows (4 floats);
+// dp: + the pattern copy's corrected diagonal;  cheb (RES 2): + the Chebyshev iterate and direction
+__host__ __device__ inline int fused_row_floats(int K, int res, int dp, int cheb = 0) {
+    return (res == 0 ? 0 : (res == 1 ? 2 * K + 1 : (res == 2 ? 4 * K + 1 : 4 * K + 5))) + (dp ? 1 : 0) + ((cheb && res == 2) ? 2 * K : 0);
+}
+inline size_t fused_smem_bytes(int K, int res, int nsl_max, int dp = 0, int cheb = 0) {
+    return FUSED_SMEM_HDR + 2 * NVMAX * 16 * 8 + fused_off_bytes(nsl_max) + (size_t)nsl_max * 32u * 4u * fused_row_floats(K, res, dp, cheb);
 }
 
-template <int K, int RES, int NW, bool PAT, int SYNC, bool PROF>
+template <int K, int RES, int NW, bool PAT, int SYNC, bool PROF, bool CHEB = false>
 __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a) {
     static_assert(K == 3 || K == 4, "z rows are float4");
     constexpr bool KEEP = (SYNC == 1);
@@ -300,8 +305,12 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
     float *r_s = fs;                                                          // [nsl_max][K][32]
     float *s_s = r_s + (size_t)nsl_max * K * 32;
     float *d_s = s_s + (size_t)nsl_max * K * 32;                              // [nsl_max][32]
-    float *x_s = d_s + (size_t)nsl_max * 32;                                  // RES = 2
+    float *x_s = d_s + (size_t)(RES >= 1 ? nsl_max : 0) * 32;                 // RES >= 2
     float *p_s = x_s + (size_t)nsl_max * K * 32;
+    float *z_s = p_s + (size_t)nsl_max * K * 32;                              // RES = 3: rows of 4 floats, the "published" vector never leaves the SM
+    float *dp_s = (RES == 3 ? z_s + (size_t)nsl_max * 128 : (RES == 2 ? z_s : (RES == 1 ? x_s : fs)));   // optional [nsl_max][32]
+    float *cy_s = dp_s + (size_t)((PAT && a.dp_smem) ? nsl_max : 0) * 32;     // CHEB && RES == 2: [nsl_max][K][32] each
+    float *cd_s = cy_s + (size_t)nsl_max * K * 32;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -332,12 +341,26 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
 
     auto R = [&](int li, int k, int row) -> float & { return RES ? r_s[((size_t)li * K + k) * 32 + lane] : a.r[(size_t)k * Vp + row]; };
     auto Sv = [&](int li, int k, int row) -> float & { return RES ? s_s[((size_t)li * K + k) * 32 + lane] : a.s[(size_t)k * Vp + row]; };
-    auto X = [&](int li, int k, int row) -> float & { return RES == 2 ? x_s[((size_t)li * K + k) * 32 + lane] : a.x[(size_t)k * Vp + row]; };
-    auto P = [&](int li, int k, int row) -> float & { return RES == 2 ? p_s[((size_t)li * K + k) * 32 + lane] : a.pv[(size_t)k * Vp + row]; };
+    auto X = [&](int li, int k, int row) -> float & { return RES >= 2 ? x_s[((size_t)li * K + k) * 32 + lane] : a.x[(size_t)k * Vp + row]; };
+    auto P = [&](int li, int k, int row) -> float & { return RES >= 2 ? p_s[((size_t)li * K + k) * 32 + lane] : a.pv[(size_t)k * Vp + row]; };
     auto Dv = [&](int li, int row) -> float { return RES ? d_s[(size_t)li * 32 + lane] : a.dinv[row]; };
+    // Chebyshev iterate (own rows) and direction: shared memory at RES = 2, else the direction lives in global planes and the
+    // own row of the iterate is read back from its published copy
+    auto CY = [&](int li, int k) -> float & { return cy_s[((size_t)li * K + k) * 32 + lane]; };
+    auto CD = [&](int li, int k, int row) -> float & { return (CHEB && RES == 2) ? cd_s[((size_t)li * K + k) * 32 + lane] : a.cd[(size_t)k * Vp + row]; };
 
     float *zcur = a.z, *zalt = a.z2;   // the published vector lives in zcur; Chebyshev steps write the next iterate to zalt and swap
-    const int cheb_m = a.cheb_m;
+    const int cheb_m = CHEB ? a.cheb_m : 0;   // the polynomial preconditioner is compiled into its own instantiations only
+    // the published rows: global memory, or (RES = 3, one CTA owns every row) shared memory
+    auto Zld = [&](int col) -> float4 {
+        if constexpr (RES == 3) return *reinterpret_cast<const float4 *>(z_s + 4 * (size_t)col);
+        else return lsp::ld_coherent4(zcur + 4 * (size_t)col);
+    };
+    auto Zst = [&](int row_, const float4 v_) {
+        if constexpr (RES == 3) *reinterpret_cast<float4 *>(z_s + 4 * (size_t)row_) = v_;
+        else *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row_) = v_;
+    };
+    const bool dp_smem = PAT && a.dp_smem != 0;
 
     long long tA = 0, tS2 = 0, tB = 0, tS1 = 0, tX = 0, t0 = 0;
     const bool prof = PROF && (a.dbg != nullptr) && tid == 0;
@@ -347,14 +370,19 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
         off_s[i] = a.soff[s_begin + i];
         if (PAT) poff_s[i] = a.poff[s_begin + i];
     }
+    if (dp_smem)
+        for (int s = s_begin + warp; s < s_end; s += NW) dp_s[(size_t)(s - s_begin) * 32 + lane] = a.diagp[s * 32 + lane];
     if (tid == 0) {
         S->nslot = 0;
         S->it = 0;
+        S->checks = 0;
         S->restarts = 0;
         S->poison = 0;
         S->cold = 0;
     }
-    __syncthreads();
+    // cluster: no CTA may write into another's shared memory before that CTA has started (compute-sanitizer flagged exactly that)
+    if constexpr (SYNC == 1) sync.barrier();
+    else __syncthreads();
 
     auto set_exponents = [&](int k, double gam, double rr) {   // thread 0
         const int eg = (gam > 0.0 && gam == gam) ? ilogb(gam) : -1000;
@@ -364,6 +392,157 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
         S->e_grr[K + k] = er;
         S->skipA[k] = S->conv[k];
         S->skipB[k] = S->skipB[K + k] = S->conv[k];
+    };
+
+    // matrix entries of this warp's first slice, (re)loaded before each wait so their latency hides under the barrier
+    int2 nv[U];
+    auto prologue = [&]() {
+        const int s = s_begin + warp;
+        if (s < s_end) {
+            const int li = s - s_begin;
+            if constexpr (PAT) {
+                const int o0 = poff_s[li], w2 = (poff_s[li + 1] - o0) >> 5;
+                const int2 *e = a.pcol + o0 + lane;
+#pragma unroll
+                for (int u = 0; u < U; ++u) nv[u] = (u < w2) ? ld_ent<KEEP>(e + u * 32) : make_int2(s * 32 + lane, s * 32 + lane);
+            } else {
+                const int o0 = off_s[li], w = (off_s[li + 1] - o0) >> 5;
+                const int2 *e = a.ent + o0 + lane;
+#pragma unroll
+                for (int u = 0; u < U; ++u) nv[u] = (u < w) ? ld_ent<KEEP>(e + u * 32) : make_int2(s * 32 + lane, 0);
+            }
+        }
+    };
+
+    // ---------------------------------------------------------------- one gather pass over the owned slices
+    // For every owned slice: t = (A y)(row) with y the published vector (zcur rows), gathered through the prefetched entries
+    // (`nv`: this slice's were loaded while the previous one was in flight; prologue() loads the first slice's before a barrier).
+    //   pre(li,row)  issues the caller's own loads right behind the gathers (same latency window),
+    //   own(li,row)  the caller's copy of row `row` of y (pattern copy only: the general copy gets it from the diagonal gather),
+    //   epi(li,row,t,yown)  consumes the result.
+    auto spmv_pass = [&](auto &&pre, auto &&own, auto &&epi) {
+        for (int s = s_begin + warp; s < s_end; s += NW) {
+            const int li = s - s_begin, row = s * 32 + lane;
+            const int sn = s + NW;
+            int2 cv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) cv[u] = nv[u];
+            float w_[K];
+            float4 zo = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (PAT) {
+                const int o0 = poff_s[li], w2 = (poff_s[li + 1] - o0) >> 5;
+                const int2 *e = a.pcol + o0 + lane;
+                float sum[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) sum[k] = 0.f;
+                float dp;
+                auto body = [&](auto ub_tag) {
+                    constexpr int UB = decltype(ub_tag)::value;
+                    float4 xa[UB], xb[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        xa[u] = Zld(cv[u].x);
+                        xb[u] = Zld(cv[u].y);
+                    }
+                    zo = own(li, row);
+                    dp = dp_smem ? dp_s[(size_t)li * 32 + lane] : a.diagp[row];
+                    pre(li, row);
+                    if (sn < s_end) {
+                        const int n0 = poff_s[li + NW], wn = (poff_s[li + NW + 1] - n0) >> 5;
+                        const int2 *en = a.pcol + n0 + lane;
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            nv[u] = (u < wn) ? ld_ent<KEEP>(en + u * 32) : make_int2(sn * 32 + lane, sn * 32 + lane);
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        const float xk[4] = {xa[u].x + xb[u].x, xa[u].y + xb[u].y, xa[u].z + xb[u].z, xa[u].w + xb[u].w};
+#pragma unroll
+                        for (int k = 0; k < K; ++k) sum[k] += xk[k];
+                    }
+                    const int extra = 2 * (UB - min(w2, UB));
+                    dp = fmaf(-a.offc, (float)extra, dp);
+                };
+                if (w2 <= 3) body(std::integral_constant<int, 3>());
+                else body(std::integral_constant<int, 4>());
+                for (int j = U; j < w2; j += U) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) cv[u] = (j + u < w2) ? ld_ent<KEEP>(e + (j + u) * 32) : make_int2(row, row);
+                    float4 xa[U], xb[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        xa[u] = Zld(cv[u].x);
+                        xb[u] = Zld(cv[u].y);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float xk[4] = {xa[u].x + xb[u].x, xa[u].y + xb[u].y, xa[u].z + xb[u].z, xa[u].w + xb[u].w};
+#pragma unroll
+                        for (int k = 0; k < K; ++k) sum[k] += xk[k];
+                    }
+                    const int extra = 2 * max(0, j + U - w2);
+                    dp = fmaf(-a.offc, (float)extra, dp);
+                }
+                const float zk[4] = {zo.x, zo.y, zo.z, zo.w};
+#pragma unroll
+                for (int k = 0; k < K; ++k) w_[k] = fmaf(dp, zk[k], a.offc * sum[k]);
+            } else {
+                const int o0 = off_s[li], w = (off_s[li + 1] - o0) >> 5;
+                const int2 *e = a.ent + o0 + lane;
+#pragma unroll
+                for (int k = 0; k < K; ++k) w_[k] = 0.f;
+                {
+                    float4 xv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) xv[u] = Zld(cv[u].x);
+                    pre(li, row);
+                    if (sn < s_end) {
+                        const int n0 = off_s[li + NW], wn = (off_s[li + NW + 1] - n0) >> 5;
+                        const int2 *en = a.ent + n0 + lane;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) nv[u] = (u < wn) ? ld_ent<KEEP>(en + u * 32) : make_int2(sn * 32 + lane, 0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float wv = __int_as_float(cv[u].y);
+                        const float xk[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                        if (cv[u].x == row) zo = xv[u];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) w_[k] = fmaf(wv, xk[k], w_[k]);
+                    }
+                }
+                for (int j = U; j < w; j += U) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) cv[u] = (j + u < w) ? ld_ent<KEEP>(e + (j + u) * 32) : make_int2(row, 0);
+                    float4 xv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) xv[u] = Zld(cv[u].x);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float wv = __int_as_float(cv[u].y);
+                        const float xk[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                        if (cv[u].x == row) zo = xv[u];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) w_[k] = fmaf(wv, xk[k], w_[k]);
+                    }
+                }
+            }
+            epi(li, row, w_, zo);
+        }
+    };
+
+    // the owner's row of the published vector for phase A (pattern copy): Jacobi: D^-1 r recomputed exactly as phase B stored
+    // it; Chebyshev: the final iterate (shared memory at RES = 2, else its published row)
+    auto own_z = [&](int li, int row) -> float4 {
+        if constexpr (CHEB) {
+            if constexpr (RES == 2) return make_float4(CY(li, 0), CY(li, 1), CY(li, 2), K > 3 ? CY(li, K > 3 ? 3 : 0) : 0.f);
+            else return Zld(row);
+        } else if constexpr (RES >= 1) {
+            const float di_ = Dv(li, row);
+            return make_float4(di_ * R(li, 0, row), di_ * R(li, 1, row), di_ * R(li, 2, row), K > 3 ? di_ * R(li, K > 3 ? 3 : 0, row) : 0.f);
+        } else {
+            return Zld(row);
+        }
     };
 
     // ---------------------------------------------------------------- Chebyshev polynomial preconditioner (precond = 2)
@@ -380,55 +559,46 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 yy[k] = di * R(li, k, row);
-                a.cy[(size_t)k * Vp + row] = yy[k];
-                a.cd[(size_t)k * Vp + row] = yy[k];
+                if constexpr (RES == 2) CY(li, k) = yy[k];
+                CD(li, k, row) = yy[k];
             }
-            *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+            Zst(row, make_float4(yy[0], yy[1], yy[2], yy[3]));
         }
     };
     auto cheb_steps = [&](double (&acc2)[2 * K]) {
         for (int j = 1; j < cheb_m; ++j) {
+            prologue();                           // first slice's entries fly while the barrier completes
             sync.barrier();                       // iterate j is visible everywhere
             const float c1 = a.cheb_c1[j - 1], c2 = a.cheb_c2[j - 1];
             const bool last = (j == cheb_m - 1);
-            for (int s = s_begin + warp; s < s_end; s += NW) {
-                const int li = s - s_begin, row = s * 32 + lane;
-                const int o0 = off_s[li], w = (off_s[li + 1] - o0) >> 5;
-                const int2 *e = a.ent + o0 + lane;
-                float t[K];
+            float dprev[K];
+            spmv_pass(
+                [&](int li, int row) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) t[k] = 0.f;
-                for (int jj = 0; jj < w; jj += 4) {
-                    int2 cv[4];
-                    float4 xg[4];
+                    for (int k = 0; k < K; ++k) dprev[k] = CD(li, k, row);
+                },
+                [&](int li, int row) -> float4 {
+                    if constexpr (RES == 2) return make_float4(CY(li, 0), CY(li, 1), CY(li, 2), K > 3 ? CY(li, K > 3 ? 3 : 0) : 0.f);
+                    else return Zld(row);
+                },
+                [&](int li, int row, const float (&t)[K], const float4 &yo) {
+                    const float di = Dv(li, row);
+                    const float yk[4] = {yo.x, yo.y, yo.z, yo.w};
+                    float yy[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) cv[u] = (jj + u < w) ? ld_ent<KEEP>(e + (jj + u) * 32) : make_int2(row, 0);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) xg[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float wv = __int_as_float(cv[u].y);
-                        const float xk[4] = {xg[u].x, xg[u].y, xg[u].z, xg[u].w};
-#pragma unroll
-                        for (int k = 0; k < K; ++k) t[k] = fmaf(wv, xk[k], t[k]);
+                    for (int k = 0; k < K; ++k) {
+                        const float rk = R(li, k, row);
+                        const float dn = fmaf(c1, dprev[k], c2 * (di * (rk - t[k])));
+                        yy[k] = yk[k] + dn;
+                        CD(li, k, row) = dn;
+                        if constexpr (RES == 2) CY(li, k) = yy[k];
+                        if (last) {
+                            acc2[k] += (double)rk * (double)yy[k];
+                            acc2[K + k] += (double)rk * (double)rk;
+                        }
                     }
-                }
-                const float di = Dv(li, row);
-                float yy[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float rk = R(li, k, row);
-                    const float dn = fmaf(c1, a.cd[(size_t)k * Vp + row], c2 * (di * (rk - t[k])));
-                    yy[k] = a.cy[(size_t)k * Vp + row] + dn;
-                    a.cd[(size_t)k * Vp + row] = dn;
-                    a.cy[(size_t)k * Vp + row] = yy[k];
-                    if (last) {
-                        acc2[k] += (double)rk * (double)yy[k];
-                        acc2[K + k] += (double)rk * (double)rk;
-                    }
-                }
-                *reinterpret_cast<float4 *>(zalt + 4 * (size_t)row) = make_float4(yy[0], yy[1], yy[2], yy[3]);
-            }
+                    *reinterpret_cast<float4 *>(zalt + 4 * (size_t)row) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+                });
             float *tz = zcur;
             zcur = zalt;
             zalt = tz;
@@ -464,16 +634,18 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 acc[k] += (double)bv[k] * (double)zz[k];
                 acc[K + k] += (double)bv[k] * (double)bv[k];
             }
-            *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+            Zst(row, make_float4(zz[0], zz[1], zz[2], zz[3]));
         }
-        if (cheb_m > 1) {     // gamma = r . q(D^-1 A) D^-1 r instead of r . D^-1 r
-            double a2[2 * K];
+        if constexpr (CHEB) {
+            if (cheb_m > 1) {     // gamma = r . q(D^-1 A) D^-1 r instead of r . D^-1 r
+                double a2[2 * K];
 #pragma unroll
-            for (int i = 0; i < 2 * K; ++i) a2[i] = 0.0;
-            cheb_first();
-            cheb_steps(a2);
+                for (int i = 0; i < 2 * K; ++i) a2[i] = 0.0;
+                cheb_first();
+                cheb_steps(a2);
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = a2[k];
+                for (int k = 0; k < K; ++k) acc[k] = a2[k];
+            }
         }
         sync.template allreduce_slow<2 * K>(acc);     // fenced: also publishes z
         if (tid == 0) {
@@ -504,7 +676,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
             float xv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < K; ++k) xv[k] = X(li, k, row);
-            *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+            Zst(row, make_float4(xv[0], xv[1], xv[2], xv[3]));
         }
         sync.barrier();
         double acc[4 * K];   // [gamma | rr | floor^2 | bb]
@@ -527,7 +699,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
 #pragma unroll
                 for (int u = 0; u < 4; ++u) cv[u] = (j + u < w) ? ld_ent<KEEP>(e + (j + u) * 32) : make_int2(row, 0);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) xg[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
+                for (int u = 0; u < 4; ++u) xg[u] = Zld(cv[u].x);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float wv = __int_as_float(cv[u].y);
@@ -561,15 +733,17 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 acc[3 * K + k] += (double)bv[k] * (double)bv[k];
             }
         }
-        if (cheb_m > 1) {     // preconditioned residual norm of the new residual (the gathers of the x rows end at the first barrier inside)
-            double a2[2 * K];
+        if constexpr (CHEB) {
+            if (cheb_m > 1) {     // preconditioned residual norm of the new residual (the gathers of the x rows end at the first barrier inside)
+                double a2[2 * K];
 #pragma unroll
-            for (int i = 0; i < 2 * K; ++i) a2[i] = 0.0;
-            sync.barrier();
-            cheb_first();
-            cheb_steps(a2);
+                for (int i = 0; i < 2 * K; ++i) a2[i] = 0.0;
+                sync.barrier();
+                cheb_first();
+                cheb_steps(a2);
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = a2[k];
+                for (int k = 0; k < K; ++k) acc[k] = a2[k];
+            }
         }
         sync.template allreduce_slow<4 * K>(acc);   // every CTA has finished gathering x rows once this returns
         if (tid == 0) {
@@ -583,7 +757,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                     if (rr > bb) worse = 1;               // guess worse than x = 0 (also caps fp32 accuracy): cold start instead
                     S->conv[k] = rr <= rtol2 * bb;
                 } else {
-                    const bool need = (rr > rtol2 * S->bb[k]) && (rr > th * th * fl2) && !(S->bb[k] == 0.0);
+                    const bool need = (rr > rtol2 * S->bb[k]) && (rr > th * th * fl2) && !(S->bb[k] == 0.0) && (S->restarts < a.refine);
                     S->conv[k] = need ? 0 : 1;
                 }
                 if (rr != rr) {
@@ -598,7 +772,10 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 set_exponents(k, gam, rr);
             }
             S->cold = (warm && worse) ? 1 : 0;
-            if (!warm) S->restarts += 1;
+            if (!warm) {
+                S->checks += 1;
+                if (!all && !bad) S->restarts += 1;
+            }
             if (bad) S->status = 3;
             else if (all) S->status = 1;
             else if (S->it >= a.maxit) S->status = 2;
@@ -621,7 +798,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                     }
                 }
                 if (cheb_m <= 1)      // (Chebyshev: the preconditioned residual is already published in zcur)
-                    *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+                    Zst(row, make_float4(zz[0], zz[1], zz[2], zz[3]));
             }
             sync.barrier();
         }
@@ -652,26 +829,6 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
         cold_init();
     }
 
-    // matrix entries of this warp's first slice, (re)loaded before each wait so their latency hides under the barrier
-    int2 nv[U];
-    auto prologue = [&]() {
-        const int s = s_begin + warp;
-        if (s < s_end) {
-            const int li = s - s_begin;
-            if constexpr (PAT) {
-                const int o0 = poff_s[li], w2 = (poff_s[li + 1] - o0) >> 5;
-                const int2 *e = a.pcol + o0 + lane;
-#pragma unroll
-                for (int u = 0; u < U; ++u) nv[u] = (u < w2) ? ld_ent<KEEP>(e + u * 32) : make_int2(s * 32 + lane, s * 32 + lane);
-            } else {
-                const int o0 = off_s[li], w = (off_s[li + 1] - o0) >> 5;
-                const int2 *e = a.ent + o0 + lane;
-#pragma unroll
-                for (int u = 0; u < U; ++u) nv[u] = (u < w) ? ld_ent<KEEP>(e + u * 32) : make_int2(s * 32 + lane, 0);
-            }
-        }
-    };
-
     for (;;) {   // episodes: iterate to convergence, check the true residual, maybe restart
         prologue();
         while (!S->stop) {
@@ -683,133 +840,29 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 float dacc_f[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) dacc_f[k] = 0.f;
-                for (int s = s_begin + warp; s < s_end; s += NW) {
-                    const int li = s - s_begin, row = s * 32 + lane;
-                    const int sn = s + NW;
-                    int2 cv[U];
+                float po[K], xo[K];
+                spmv_pass(
+                    [&](int li, int row) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) cv[u] = nv[u];
-                    float w_[K];
-                    float4 zo = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float po[K], xo[K];
-                    if constexpr (PAT) {
-                        const int o0 = poff_s[li], w2 = (poff_s[li + 1] - o0) >> 5;
-                        const int2 *e = a.pcol + o0 + lane;
-                        float sum[K];
-#pragma unroll
-                        for (int k = 0; k < K; ++k) sum[k] = 0.f;
-                        float dp;
-                        auto body = [&](auto ub_tag) {
-                            constexpr int UB = decltype(ub_tag)::value;
-                            float4 xa[UB], xb[UB];
-#pragma unroll
-                            for (int u = 0; u < UB; ++u) {
-                                xa[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
-                                xb[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].y);
-                            }
-                            zo = lsp::ld_coherent4(zcur + 4 * (size_t)row);
-                            dp = a.diagp[row];
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                po[k] = P(li, k, row);
-                                xo[k] = X(li, k, row);
-                            }
-                            if (sn < s_end) {
-                                const int n0 = poff_s[li + NW], wn = (poff_s[li + NW + 1] - n0) >> 5;
-                                const int2 *en = a.pcol + n0 + lane;
-#pragma unroll
-                                for (int u = 0; u < U; ++u)
-                                    nv[u] = (u < wn) ? ld_ent<KEEP>(en + u * 32) : make_int2(sn * 32 + lane, sn * 32 + lane);
-                            }
-#pragma unroll
-                            for (int u = 0; u < UB; ++u) {
-                                const float xk[4] = {xa[u].x + xb[u].x, xa[u].y + xb[u].y, xa[u].z + xb[u].z, xa[u].w + xb[u].w};
-#pragma unroll
-                                for (int k = 0; k < K; ++k) sum[k] += xk[k];
-                            }
-                            const int extra = 2 * (UB - min(w2, UB));
-                            dp = fmaf(-a.offc, (float)extra, dp);
-                        };
-                        if (w2 <= 3) body(std::integral_constant<int, 3>());
-                        else body(std::integral_constant<int, 4>());
-                        for (int j = U; j < w2; j += U) {
-#pragma unroll
-                            for (int u = 0; u < U; ++u) cv[u] = (j + u < w2) ? ld_ent<KEEP>(e + (j + u) * 32) : make_int2(row, row);
-                            float4 xa[U], xb[U];
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                xa[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
-                                xb[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].y);
-                            }
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                const float xk[4] = {xa[u].x + xb[u].x, xa[u].y + xb[u].y, xa[u].z + xb[u].z, xa[u].w + xb[u].w};
-#pragma unroll
-                                for (int k = 0; k < K; ++k) sum[k] += xk[k];
-                            }
-                            const int extra = 2 * max(0, j + U - w2);
-                            dp = fmaf(-a.offc, (float)extra, dp);
+                        for (int k = 0; k < K; ++k) {
+                            po[k] = P(li, k, row);
+                            xo[k] = X(li, k, row);
                         }
+                    },
+                    own_z,
+                    [&](int li, int row, const float (&w_)[K], const float4 &zo) {
                         const float zk[4] = {zo.x, zo.y, zo.z, zo.w};
 #pragma unroll
-                        for (int k = 0; k < K; ++k) w_[k] = fmaf(dp, zk[k], a.offc * sum[k]);
-                    } else {
-                        const int o0 = off_s[li], w = (off_s[li + 1] - o0) >> 5;
-                        const int2 *e = a.ent + o0 + lane;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) w_[k] = 0.f;
-                        {
-                            float4 xv[U];
-#pragma unroll
-                            for (int u = 0; u < U; ++u) xv[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                po[k] = P(li, k, row);
-                                xo[k] = X(li, k, row);
-                            }
-                            if (sn < s_end) {
-                                const int n0 = off_s[li + NW], wn = (off_s[li + NW + 1] - n0) >> 5;
-                                const int2 *en = a.ent + n0 + lane;
-#pragma unroll
-                                for (int u = 0; u < U; ++u) nv[u] = (u < wn) ? ld_ent<KEEP>(en + u * 32) : make_int2(sn * 32 + lane, 0);
-                            }
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                const float wv = __int_as_float(cv[u].y);
-                                const float xk[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-                                if (cv[u].x == row) zo = xv[u];
-#pragma unroll
-                                for (int k = 0; k < K; ++k) w_[k] = fmaf(wv, xk[k], w_[k]);
-                            }
+                        for (int k = 0; k < K; ++k) {
+                            const float al = S->alpha[k], be = S->beta[k];
+                            X(li, k, row) = fmaf(al, po[k], xo[k]);               // x += alpha_prev p   (the previous iteration's pair)
+                            const float pn = fmaf(be, po[k], zk[k]);                // p = z + beta p
+                            const float sn_ = fmaf(be, Sv(li, k, row), w_[k]);      // s = A z + beta s  (= A p)
+                            P(li, k, row) = pn;
+                            Sv(li, k, row) = sn_;
+                            dacc_f[k] = fmaf(pn, sn_, dacc_f[k]);
                         }
-                        for (int j = U; j < w; j += U) {
-#pragma unroll
-                            for (int u = 0; u < U; ++u) cv[u] = (j + u < w) ? ld_ent<KEEP>(e + (j + u) * 32) : make_int2(row, 0);
-                            float4 xv[U];
-#pragma unroll
-                            for (int u = 0; u < U; ++u) xv[u] = lsp::ld_coherent4(zcur + 4 * (size_t)cv[u].x);
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                const float wv = __int_as_float(cv[u].y);
-                                const float xk[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-                                if (cv[u].x == row) zo = xv[u];
-#pragma unroll
-                                for (int k = 0; k < K; ++k) w_[k] = fmaf(wv, xk[k], w_[k]);
-                            }
-                        }
-                    }
-                    const float zk[4] = {zo.x, zo.y, zo.z, zo.w};
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const float al = S->alpha[k], be = S->beta[k];
-                        X(li, k, row) = fmaf(al, po[k], xo[k]);               // x += alpha_prev p   (the previous iteration's pair)
-                        const float pn = fmaf(be, po[k], zk[k]);                // p = z + beta p
-                        const float sn_ = fmaf(be, Sv(li, k, row), w_[k]);      // s = A z + beta s  (= A p)
-                        P(li, k, row) = pn;
-                        Sv(li, k, row) = sn_;
-                        dacc_f[k] = fmaf(pn, sn_, dacc_f[k]);
-                    }
-                }
+                    });
                 double dacc[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) dacc[k] = (double)dacc_f[k];
@@ -836,16 +889,21 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 double acc2[2 * K];
 #pragma unroll
                 for (int i = 0; i < 2 * K; ++i) acc2[i] = 0.0;
-                if (cheb_m > 1) {
-                    for (int s = s_begin + warp; s < s_end; s += NW) {
-                        const int li = s - s_begin, row = s * 32 + lane;
+                bool preconditioned = false;
+                if constexpr (CHEB) {
+                    if (cheb_m > 1) {
+                        for (int s = s_begin + warp; s < s_end; s += NW) {
+                            const int li = s - s_begin, row = s * 32 + lane;
 #pragma unroll
-                        for (int k = 0; k < K; ++k) R(li, k, row) = fmaf(-alpha[k], Sv(li, k, row), R(li, k, row));
+                            for (int k = 0; k < K; ++k) R(li, k, row) = fmaf(-alpha[k], Sv(li, k, row), R(li, k, row));
+                        }
+                        __syncwarp();
+                        cheb_first();
+                        cheb_steps(acc2);
+                        preconditioned = true;
                     }
-                    __syncwarp();
-                    cheb_first();
-                    cheb_steps(acc2);
-                } else
+                }
+                if (!preconditioned)
                 for (int s = s_begin + warp; s < s_end; s += NW) {
                     const int li = s - s_begin, row = s * 32 + lane;
                     const float di = Dv(li, row);
@@ -859,7 +917,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                         acc2[k] += (double)(di * r2);
                         acc2[K + k] += (double)r2;
                     }
-                    *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+                    Zst(row, make_float4(zz[0], zz[1], zz[2], zz[3]));
                 }
                 if (prof) { const long long t1 = clock64(); tB += t1 - t0; t0 = t1; }
                 auto postB = [&](const double gn, const double rrn) {   // beta, convergence, stop decision
@@ -917,7 +975,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
             }
         }
         __syncthreads();
-        const bool check = (S->status == 1) && (S->restarts < a.refine) && (S->it > 0);
+        const bool check = (S->status == 1) && (a.refine > 0) && (S->checks <= a.refine) && (S->it > 0);
         if (!check) break;
         sync.barrier();           // all gathers of z are over before the buffer is reused for the x rows
         restart_from_x(false);

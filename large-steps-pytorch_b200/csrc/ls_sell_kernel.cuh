@@ -36,6 +36,7 @@ struct SellArgs {
     double *partials;       // [K][gridDim.x]
     unsigned int *ticket;
     double *dot_out;        // [K]
+    int pf_halo;            // TMA kernel: rows of p beyond the CTA's own range to pull into L2 with a bulk prefetch (0 = off)
 };
 
 template <int K> struct PRow;
@@ -192,8 +193,8 @@ inline size_t sell_tma_smem_bytes(int nw, int depth) {
     return (size_t)nw * depth * SELL_SLOT_BYTES + (size_t)nw * depth * 8 + 2048;   // rings, mbarriers, reduction scratch
 }
 
-template <int K, bool DOT, int NW, int DEPTH>
-__global__ void __launch_bounds__(NW * 32, 1) spmm_sell_tma_kernel(const SellArgs a) {
+template <int K, bool DOT, int NW, int DEPTH, int MINB = 1>
+__global__ void __launch_bounds__(NW * 32, MINB) spmm_sell_tma_kernel(const SellArgs a) {
     typedef typename PRow<K>::T PT;
     constexpr int U = 8;
     extern __shared__ __align__(128) unsigned char sm_raw[];
@@ -251,6 +252,19 @@ __global__ void __launch_bounds__(NW * 32, 1) spmm_sell_tma_kernel(const SellArg
     }
     // the matrix never changes between launches; the vectors do: wait for the previous kernel before touching them
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (a.pf_halo > 0 && warp < 8) {
+        // HBM-cold launches: every slice's gathers used to wait a full DRAM round trip for the first touch of its p lines
+        // (~2 us x 6.6 slices per warp).  The rows this CTA gathers are its own range plus a halo: pull them into L2 with a
+        // handful of bulk prefetches (UBLKPF.L2) so that the gathers that follow hit L2.
+        const long long r0 = max(0LL, (long long)s_begin * 32 - a.pf_halo), r1 = min((long long)a.nslices * 32, (long long)s_end * 32 + a.pf_halo);
+        const long long bytes = (r1 - r0) * (long long)sizeof(PT);
+        const char *base = reinterpret_cast<const char *>(a.p) + r0 * (long long)sizeof(PT);
+        constexpr int CH = 16384;
+        for (long long off = (long long)warp * CH; off < bytes; off += 8LL * CH) {
+            const unsigned int nb = (unsigned int)min((long long)CH, bytes - off) & ~15u;
+            if (lane == 0 && nb > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(nb) : "memory");
+        }
+    }
     if (a.done != nullptr && *reinterpret_cast<const volatile int *>(a.done) != 0) {
         // converged earlier in this graph chunk: nothing to do, but the bulk copies already in flight must land before the
         // CTA (and its shared memory) goes away

@@ -28,7 +28,9 @@ def cache_put(key, value, A):
 
 
 class _SpMM(torch.autograd.Function):
-    """y = M x through the library's CSR SpMM; backward uses M^T = M only for the dense operand."""
+    """y = M x through the library's CSR SpMM.  The backward applies M itself: every matrix this package builds (system
+    matrices, both Laplacians) is symmetric, like the reference's (geometry.py:56,94); a non-symmetric foreign matrix would
+    need M^T and must go through torch's own `L @ v`."""
 
     @staticmethod
     def forward(ctx, L, v):
@@ -45,6 +47,8 @@ def spmm(L, v):
     """Non-differentiable y = L @ v on the device (ls_spmm_csr_f32). v: (V,k) or (V,) float32 CUDA."""
     rowptr, col, val = csr_of(L)
     N.require_cuda(v, "v")
+    if v.device != val.device:
+        raise RuntimeError(f"v is on {v.device} but the matrix is on {val.device}")
     if v.dtype != torch.float32:
         raise TypeError(f"v must be float32, got {v.dtype}")
     squeeze = v.dim() == 1

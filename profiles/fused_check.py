@@ -35,7 +35,7 @@ else:
 dev = "cuda:0"
 tv, tf = torch.from_numpy(v).to(dev), torch.from_numpy(f).to(dev)
 M = compute_matrix(tv, tf, **kw)
-s = PCGSolver(M, check=False)
+s = PCGSolver(M, check=False, precond=os.environ.get("CHK_PRECOND", "jacobi"))
 out = {"env": {k: v_ for k, v_ in os.environ.items() if k.startswith(("LS_", "CHK_"))}, "V": int(M.shape[0]), "desc": s.describe()}
 r, c, val, V = oracle.compute_matrix(v, f, **kw)
 A = oracle.coo_to_scipy(r, c, val, V)

@@ -50,8 +50,8 @@ def timeit(which, handles, reps=400):
 
 
 out = {"env": {k: v for k, v in os.environ.items() if k.startswith(("LS_", "PROBE_"))}, "n": n, "desc": hs[0].describe()}
-names = ["spmm", "update", "pupdate", "iter3"]
-for w in range(4):
+names = ["spmm", "update", "pupdate", "iter3", "spmv_nodot"]
+for w in range(5):
     out[names[w] + "_cold_us"] = round(timeit(w, hs), 2)
     out[names[w] + "_hot_us"] = round(timeit(w, hs[:1]), 2)
 B = hs[0].spmm_bytes(3)

@@ -42,6 +42,21 @@ def test_adam_uniform_large_and_param_groups():
             np.testing.assert_allclose(p.detach().cpu().numpy(), cur[i], rtol=0, atol=1e-6)
 
 
+def test_adam_uniform_propagates_nan():
+    """optimize.py:40 takes max(sqrt(m2)) with torch.max, which propagates NaN: one NaN gradient poisons every parameter and
+    the divergence is visible.  (A plain fmaxf reduction would drop it.)"""
+    p = torch.nn.Parameter(torch.ones(5000, 3, device=DEV))
+    opt = AdamUniform([p], lr=0.1)
+    g = torch.randn(5000, 3, device=DEV)
+    p.grad = g.clone()
+    opt.step()
+    assert torch.isfinite(p).all()
+    g[1234, 1] = float("nan")
+    p.grad = g
+    opt.step()
+    assert torch.isnan(p).all()
+
+
 def test_tutorial_shaped_loop_tracks_cpu_oracle():
     """Stand-in for suzanne->target (scenes and nvdiffrast are not available): source icosphere, target = displaced
     sphere with the same connectivity, loss = mean (v - v_target)^2 (the L2 image loss option of scripts/main.py:188;

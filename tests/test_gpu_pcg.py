@@ -209,7 +209,8 @@ def test_morton_reorder_is_transparent(bunny_mesh):
 
 
 MODES = [
-    {},                                                         # default: fused kernel; cluster for these sizes, pattern copy if uniform
+    {},                                                         # default: fused kernel on the cooperative grid (one CTA for tiny meshes), pattern copy if uniform
+    {"LS_PCG_CLUSTER": "16"},                                   # one thread-block cluster of 16 CTAs (DSMEM all-reduce, barrier.cluster)
     {"LS_PCG_CLUSTER": "0"},                                    # fused, cooperative grid, everything in shared memory (256-thread CTAs)
     {"LS_PCG_CLUSTER": "0", "LS_PCG_SMALLCTA": "0"},            # ... 768-thread CTAs
     {"LS_PCG_CLUSTER": "0", "LS_PCG_RES": "1"},                 # ... x / p in global memory
@@ -235,7 +236,8 @@ def test_every_solver_mode_meets_the_bar(env, bunny_mesh, monkeypatch):
     for k_, v_ in env.items():
         monkeypatch.setenv(k_, v_)
     cases = [config2(bunny_mesh), (*workloads.plane(260, seed=1), dict(lambda_=1.0, alpha=0.95)),
-             (*workloads.icosphere(5), dict(lambda_=10.0))]
+             (*workloads.icosphere(5), dict(lambda_=10.0)), (*workloads.icosphere(3), dict(lambda_=10.0)),
+             (*workloads.plane(50, seed=2), dict(lambda_=19.0, cotan=True))]
     for v, f, kw in cases:
         (r, c, val, V), ds = direct_for(v, f, kw)
         _, b, g = rhs(r, c, val, V, v)
@@ -251,17 +253,21 @@ def test_every_solver_mode_meets_the_bar(env, bunny_mesh, monkeypatch):
         else:
             assert d["algo"] == "fused"
             assert d["sell_engine"] == (2 if uniform and env.get("LS_PCG_PATTERN") != "0" else 1)
+            tiny = V <= 96 * 32                      # <= 96 slices: one CTA holds everything, gathered vector included
             if env.get("LS_PCG_CLUSTER") == "0":
-                assert d["cluster"] == 0 and d["grid"] > 16
+                assert d["cluster"] == 0 and d["grid"] == min(148, (V + 31) // 32)
                 assert d["residency"] == int(env.get("LS_PCG_RES", "2"))
-                assert d["threads"] == (768 if env.get("LS_PCG_SMALLCTA") == "0" or d["residency"] < 2 else 256)
+                if not tiny:
+                    assert d["threads"] == (768 if env.get("LS_PCG_SMALLCTA") == "0" or d["residency"] < 2 else 256)
             elif "LS_PCG_CLUSTER" in env:
                 assert d["cluster"] in (0, int(env["LS_PCG_CLUSTER"]))
                 if V < 20000:
                     assert d["cluster"] == int(env["LS_PCG_CLUSTER"])
+            elif tiny:
+                assert d["cluster"] == 1 and d["grid"] == 1 and d["residency"] == int(env.get("LS_PCG_RES", "3"))
             else:
-                assert d["cluster"] == 16 and d["residency"] == 2
-        if "LS_FORCE_REORDER" in env:
+                assert d["cluster"] == 0 and d["grid"] == 148 and d["residency"] == 2
+        if "LS_FORCE_REORDER" in env and V >= 8192:      # (smaller meshes carry no Morton order: everything is cache resident)
             assert d["reordered"] == 1
         assert rel_l2(s.solve(t(b)).cpu().numpy(), ds.solve(b)) < BAR, (env, kw)
         assert 0 < s.iterations < 1000 and max(s.relres[:3]) <= 5e-5     # relres is the TRUE residual once the guard has run
@@ -273,6 +279,39 @@ def test_every_solver_mode_meets_the_bar(env, bunny_mesh, monkeypatch):
         b2 = (b + 1e-3 * np.random.default_rng(7).normal(size=b.shape)).astype(np.float32)
         assert rel_l2(w.solve(t(b2)).cpu().numpy(), ds.solve(b2)) < BAR, (env, kw)
         assert w.iterations < it_cold
+
+
+@pytest.mark.parametrize("env", [{}, {"LS_PCG_CLUSTER": "0", "LS_PCG_RES": "1"}, {"LS_PCG_CLUSTER": "0", "LS_PCG_RES": "0"},
+                                 {"LS_PCG_CLUSTER": "8"}], ids=["default", "res1", "res0", "cluster8"])
+def test_chebyshev_preconditioner(env, bunny_mesh, monkeypatch):
+    """precond = 2: a degree-3 Chebyshev polynomial in D^-1 M on top of Jacobi.  Same answers; at alpha = 0.999
+    (kappa ~ 1.2e4) at most a third of the Jacobi iterations, i.e. a third of the all-reduces."""
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    cases = [(*workloads.plane(200, seed=0), dict(lambda_=1.0, alpha=0.999)), config2(bunny_mesh),
+             (*workloads.icosphere(3), dict(lambda_=10.0))]
+    for v, f, kw in cases:
+        (r, c, val, V), ds = direct_for(v, f, kw)
+        _, b, g = rhs(r, c, val, V, v)
+        M = compute_matrix(*to_dev(v, f), **kw)
+        sj = PCGSolver(M)
+        xj = sj.solve(t(b))
+        itj = sj.iterations
+        sc = PCGSolver(M, precond="chebyshev")
+        assert sc.describe()["algo"] == "fused"
+        xc = sc.solve(t(b))
+        itc = sc.iterations
+        print(f"V={V} {kw}: Jacobi {itj} iterations, Chebyshev {itc}")
+        assert rel_l2(xc.cpu().numpy(), ds.solve(b)) < BAR and rel_l2(xj.cpu().numpy(), ds.solve(b)) < BAR
+        assert rel_l2(sc.solve(t(g), backward=True).cpu().numpy(), ds.solve(g)) < BAR
+        assert itc <= (itj + 2) // 3 + 2, (itj, itc)
+        assert torch.equal(sc.solve(t(b)), xc)          # deterministic
+        w = PCGSolver(M, precond="chebyshev", warm_start=True)
+        w.solve(t(b))
+        b2 = (b + 1e-3 * np.random.default_rng(7).normal(size=b.shape)).astype(np.float32)
+        assert rel_l2(w.solve(t(b2)).cpu().numpy(), ds.solve(b2)) < BAR and w.iterations <= itc
+    with pytest.raises(ValueError, match="Unknown preconditioner"):
+        PCGSolver(M, precond="ic0")
 
 
 def test_two_live_solvers_of_different_size():
