@@ -95,7 +95,9 @@ int ls_spmm_csr_f32(int64_t V, const int32_t *rowptr, const int32_t *col, const 
  *       numbering), extracts the Jacobi diagonal, balances the row partition, plans the SpMM blocks.
  *       The caller keeps `workspace` alive until ls_pcg_destroy.  Synchronises `stream`.
  *       precond: 0 = none, 1 = Jacobi, 2 = Chebyshev polynomial of degree 3 in D^-1 M on top of Jacobi (spectrum bounds from a
- *       Gershgorin row scan; ~3x fewer CG iterations and reductions for ~1.3x the SpMVs).   k_max in [1,4].
+ *       Gershgorin row scan; ~3x fewer CG iterations and reductions for ~1.3x the SpMVs), 3 = auto: 2 where it is measured
+ *       faster (meshes whose solver vectors fit in shared memory on the cooperative grid, ~1K..430K vertices), else 1.
+ *       k_max in [1,4].
  *       The workspace size depends on (V, nnz, k_max) only -- never on the environment.
  *   ls_pcg_solve:  b, x: (V,k) float32 row-major contiguous (ld = k); x0 = NULL for a cold start (x0 may alias x).
  *       rtol: stop when ||r_j||_2 <= rtol * ||b_j||_2 for every column j (columns freeze independently, which
@@ -119,7 +121,7 @@ int ls_pcg_destroy(void *handle);
 int ls_pcg_set_refinement(void *handle, int max_restarts, float theta);
 /* introspection.  Fused solver (default): out8 = [matrix copy (2 pattern-only SELL-32 / 1 general SELL-32), padded SELL
  *   entries, CTAs, cluster size (0 = cooperative grid), 10 + residency level (0 vectors in global memory, 1 r/s/D^-1 in
- *   shared memory, 2 also x and p), CTAs, threads per CTA, re-ordered].
+ *   shared memory, 2 also x and p, 3 also the gathered vector), preconditioner in use (0 / 1 / 2), threads per CTA, re-ordered].
  *   Older paths (LS_PCG_ALGO=classic / LS_PCG_MODE=graph): out8 = [engine (2, 1, 0 = TMA-staged CSR), padded SELL entries,
  *   SpMM grid, vector-kernel grid, mode (0 graph of 3 kernels / 1 persistent, r+Ap global / 2 persistent, r+Ap in smem),
  *   persistent grid, block plan valid, re-ordered]                                                                   */

@@ -955,7 +955,9 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
     // give 16 x ~28 B/clk of L2 bandwidth and cluster.sync flushes L1 each time, so it is opt-in (LS_PCG_CLUSTER=N).
     int cs = 0;
     if (want_cluster != 0) {
-        if (h->nslices <= 4 * W) cs = 1;
+        // one CTA only while every warp has at most one slice: beyond that the single SM is instruction-issue bound (81 slices: 8.4 k
+        // cycles for phase A alone) and the cooperative grid wins despite its ~2 x 3.5 k cycles of synchronisation per iteration
+        if (h->nslices <= env_int("LS_PCG_ONECTA", W)) cs = 1;
         if (want_cluster > 0) cs = want_cluster;
         if (cs > 0 && (h->nslices + cs - 1) / cs > cap2) cs = 0;
     }
@@ -1208,7 +1210,7 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
     *handle_out = nullptr;
     LS_REQUIRE(V > 0 && nnz > 0 && V < (int64_t)0x7ffffff0 && nnz < (int64_t)0x7ffffff0, "size out of range");
     LS_REQUIRE(k_max >= 1 && k_max <= KMAX, "k_max must be in [1,4]");
-    LS_REQUIRE(precond >= 0 && precond <= 2, "precond must be 0 (none), 1 (Jacobi) or 2 (Chebyshev polynomial over Jacobi)");
+    LS_REQUIRE(precond >= 0 && precond <= 3, "precond must be 0 (none), 1 (Jacobi), 2 (Chebyshev polynomial over Jacobi) or 3 (auto)");
     LS_REQUIRE(rowptr && col && val, "NULL CSR pointer");
     LS_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 255) == 0, "workspace NULL or not 256-byte aligned");
     LsDevInfo di;
@@ -1365,6 +1367,15 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
     }
 
     float hgersh = 0.f;
+    if (precond == 3) {
+        // auto: the polynomial pays where the iteration is synchronisation-bound and its vectors fit in shared memory -- the
+        // cooperative grid at residency level 2 (measured: 4K..250K vertices 13-26 % faster, V = 1e6 13 % slower, one CTA slower)
+        const int g = di.sm_count < h->nslices ? di.sm_count : h->nslices;
+        const int nsl_max = (h->nslices + g - 1) / g;
+        const bool fits = lsf::fused_smem_bytes(3, 2, nsl_max, 1, 1) <= (size_t)di.max_smem_optin;
+        precond = (h->nslices > env_int("LS_PCG_ONECTA", lsp::PWARPS) && fits) ? 2 : 1;
+        h->precond = precond;
+    }
     if (precond == 2) {
         TRY_OR_FAIL(cudaMemsetAsync(h->gersh, 0, 64, stream));
         k_gershgorin<<<(unsigned)((V + 255) / 256), 256, 0, stream>>>(V, h->rowptr, h->col, h->val, h->gersh);
@@ -1655,13 +1666,13 @@ extern "C" int ls_pcg_describe(void *handle, int64_t *out8) {
     PcgHandle *h = (PcgHandle *)handle;
     LS_REQUIRE(h != nullptr && out8 != nullptr, "NULL pointer");
     const PcgHandle::FusedCfg &fc = h->fused[0];
-    if (fc.on) {   // fused two-synchronisation solver: [engine, padded entries, grid, cluster size, mode 10 + RES, grid, threads, re-ordered]
+    if (fc.on) {   // fused two-synchronisation solver: [engine, padded entries, grid, cluster size, mode 10 + RES, preconditioner, threads, re-ordered]
         out8[0] = fc.pat ? 2 : 1;
         out8[1] = h->sell_entries;
         out8[2] = fc.grid;
         out8[3] = fc.cluster;
         out8[4] = 10 + fc.res;
-        out8[5] = fc.grid;
+        out8[5] = (h->cheb_m > 1) ? 2 : h->precond;    // preconditioner actually in use (auto resolved)
         out8[6] = fc.nw * 32;
         out8[7] = h->has_perm;
         return LS_OK;

@@ -41,7 +41,8 @@ class PCGSolver(Solver):
     M : torch.sparse_coo_tensor   system matrix (compute_matrix output, or any coalesced SPD float32 COO on CUDA)
     rtol : float     stop when ||r_j|| <= rtol ||b_j|| for every column j
     maxit : int      iteration cap (the reference CG has none and can spin forever, solvers.py:73)
-    precond : {'jacobi', 'none', 'chebyshev'}   'chebyshev': degree-3 Chebyshev polynomial in D^-1 M on top of Jacobi (C ABI precond = 2):
+    precond : {'jacobi', 'none', 'chebyshev', 'auto'}   'auto': chebyshev where it is measured faster (mid-size meshes), else jacobi.
+                     'chebyshev': degree-3 Chebyshev polynomial in D^-1 M on top of Jacobi (C ABI precond = 2):
                      ~3x fewer CG iterations and all-reduces, ~1.3x more SpMVs (each with one grid barrier, no reduction)
     warm_start : bool   keep the previous solution as the next initial guess, separately for forward and backward
                         solves, as the reference CG does (solvers.py:102-110,120-124)
@@ -59,7 +60,7 @@ class PCGSolver(Solver):
 
     def __init__(self, M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, strict=False, reorder=True,
                  check=True, refine=1, theta=3.0, workspace=None):
-        if precond not in ("jacobi", "none", "chebyshev"):
+        if precond not in ("jacobi", "none", "chebyshev", "auto"):
             raise ValueError(f"Unknown preconditioner '{precond}'.")
         rowptr, col, val = csr_of(M)
         order = order_of(M) if reorder else None
@@ -90,7 +91,7 @@ class PCGSolver(Solver):
                     raise ValueError(f"workspace must be a 256-byte aligned uint8 tensor of >= {nbytes.value} bytes on {self.device}")
                 self._ws = workspace
             N.check(lib.ls_pcg_create(ctypes.byref(self._handle), self.V, self.nnz, N.ptr(rowptr), N.ptr(col),
-                                      N.ptr(val), N.ptr(order), {"none": 0, "jacobi": 1, "chebyshev": 2}[precond], K_MAX, N.ptr(self._ws),
+                                      N.ptr(val), N.ptr(order), {"none": 0, "jacobi": 1, "chebyshev": 2, "auto": 3}[precond], K_MAX, N.ptr(self._ws),
                                       nbytes.value, N.stream_ptr(self.device)), "ls_pcg_create")
             N.check(lib.ls_pcg_set_refinement(self._handle, int(refine), float(theta)), "ls_pcg_set_refinement")
 
@@ -166,7 +167,8 @@ class PCGSolver(Solver):
         o = [int(v) for v in out]
         if o[4] >= 10:    # fused two-synchronisation solver (csrc/ls_pcg_fused.cuh)
             return {"algo": "fused", "sell_engine": o[0], "sell_entries": o[1], "grid": o[2], "cluster": o[3],
-                    "residency": o[4] - 10, "threads": o[6], "reordered": o[7],
+                    "residency": o[4] - 10, "precond": {0: "none", 1: "jacobi", 2: "chebyshev"}.get(o[5], o[5]), "threads": o[6],
+                    "reordered": o[7],
                     "persistent": 2 if o[4] - 10 >= 1 else 1, "persistent_grid": o[2]}
         keys = ("sell_engine", "sell_entries", "spmm_grid", "vec_grid", "persistent", "persistent_grid", "planned", "reordered")
         d = dict(zip(keys, o))
@@ -276,7 +278,7 @@ class CholeskySolver(PCGSolver):
 
     def __init__(self, M, workspace=None):
         # like cholespy's solve, the call is asynchronous; a solve that did not converge is reported at the next call
-        super().__init__(M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=False, check=False, refine=1,
+        super().__init__(M, rtol=1e-7, maxit=10000, precond="auto", warm_start=False, check=False, refine=1,
                          workspace=workspace)
 
 
@@ -285,7 +287,7 @@ class ConjugateGradientSolver(PCGSolver):
     warm starts; uses a *relative* tolerance and an iteration cap instead of the reference's absolute 1e-5."""
 
     def __init__(self, M, workspace=None):
-        super().__init__(M, rtol=1e-7, maxit=10000, precond="jacobi", warm_start=True, workspace=workspace)
+        super().__init__(M, rtol=1e-7, maxit=10000, precond="auto", warm_start=True, workspace=workspace)
 
 
 class DifferentiableSolve(Function):

@@ -20,7 +20,8 @@ def cases(bunny_mesh):
     bv, bf = workloads.subdivide(*bunny_mesh)
     return [("fan21", *fan_mesh(21), dict(lambda_=3.0)),                                   # valence 21: the wide-slice loop
             ("plane64", *workloads.plane(64, seed=0), dict(lambda_=19.0)),               # 128 slices: the cooperative grid, one slice per CTA
-            ("plane40", *workloads.plane(40, seed=0), dict(lambda_=19.0)),               # single CTA, everything in shared memory
+            ("plane26", *workloads.plane(26, seed=0), dict(lambda_=19.0)),               # 22 slices: single CTA, everything in shared memory
+            ("plane40", *workloads.plane(40, seed=0), dict(lambda_=19.0)),               # 50 slices: 50 CTAs of one slice each
             ("plane300", *workloads.plane(300, seed=0), dict(lambda_=19.0)),             # cooperative grid
             ("bunny_x1", bv.astype(np.float32), bf, dict(lambda_=1.0, alpha=0.9)),       # irregular valence
             ("plane300_cot", *workloads.plane(300, seed=0), dict(lambda_=19.0, cotan=True))]   # not uniform: general copy

@@ -253,7 +253,7 @@ def test_every_solver_mode_meets_the_bar(env, bunny_mesh, monkeypatch):
         else:
             assert d["algo"] == "fused"
             assert d["sell_engine"] == (2 if uniform and env.get("LS_PCG_PATTERN") != "0" else 1)
-            tiny = V <= 96 * 32                      # <= 96 slices: one CTA holds everything, gathered vector included
+            tiny = V <= 24 * 32                      # <= 24 slices (one per warp): one CTA holds everything, gathered vector included
             if env.get("LS_PCG_CLUSTER") == "0":
                 assert d["cluster"] == 0 and d["grid"] == min(148, (V + 31) // 32)
                 assert d["residency"] == int(env.get("LS_PCG_RES", "2"))
@@ -266,7 +266,7 @@ def test_every_solver_mode_meets_the_bar(env, bunny_mesh, monkeypatch):
             elif tiny:
                 assert d["cluster"] == 1 and d["grid"] == 1 and d["residency"] == int(env.get("LS_PCG_RES", "3"))
             else:
-                assert d["cluster"] == 0 and d["grid"] == 148 and d["residency"] == 2
+                assert d["cluster"] == 0 and d["grid"] == min(148, (V + 31) // 32) and d["residency"] == 2
         if "LS_FORCE_REORDER" in env and V >= 8192:      # (smaller meshes carry no Morton order: everything is cache resident)
             assert d["reordered"] == 1
         assert rel_l2(s.solve(t(b)).cpu().numpy(), ds.solve(b)) < BAR, (env, kw)
@@ -312,6 +312,16 @@ def test_chebyshev_preconditioner(env, bunny_mesh, monkeypatch):
         assert rel_l2(w.solve(t(b2)).cpu().numpy(), ds.solve(b2)) < BAR and w.iterations <= itc
     with pytest.raises(ValueError, match="Unknown preconditioner"):
         PCGSolver(M, precond="ic0")
+
+
+def test_auto_preconditioner_choice(bunny_mesh):
+    """from_differential's plug-ins use precond='auto': Chebyshev where it is measured faster (cooperative grid with every solver
+    vector in shared memory), Jacobi for one-CTA meshes and for meshes too large for that residency level."""
+    for (v, f, kw), want in ((config2(bunny_mesh), "chebyshev"), ((*workloads.icosphere(3), dict(lambda_=10.0)), "jacobi"),
+                             ((*workloads.plane(800, seed=0), dict(lambda_=1.0, alpha=0.95)), "jacobi")):
+        M = compute_matrix(*to_dev(v, f), **kw)
+        assert CholeskySolver(M).describe()["precond"] == want
+        assert PCGSolver(M).describe()["precond"] == "jacobi"
 
 
 def test_two_live_solvers_of_different_size():
