@@ -1,13 +1,16 @@
-// ls_pcg.cu -- Jacobi-preconditioned conjugate gradients for M X = B, all K columns in one pass (sm_100a):
-// handle / workspace management, the graph-mode solver and the C entry points.
+// ls_pcg.cu -- preconditioned conjugate gradients for M X = B, all K columns in one pass (sm_100a):
+// handle / workspace management, solver configuration, the graph-mode solver and the C entry points.
 //
 // Replaces the reference's solve plug-ins (largesteps/solvers.py:26-39 CholeskySolver -> cholespy/CHOLMOD,
 // solvers.py:41-126 ConjugateGradientSolver -> ~12 eager torch kernels + 1 host sync per iteration per axis).
 //
-// Two execution modes share the handle, the data layout and the arithmetic:
-//   * persistent (ls_pcg_persistent.cuh): the whole solve is ONE cooperative kernel -- the default for K = 3;
+// Three execution modes share the handle, the data layout and the per-column arithmetic:
+//   * fused (ls_pcg_fused.cuh): the whole solve is ONE kernel with two grid synchronisations per iteration, in-kernel warm
+//     start and true-residual guard, optional Chebyshev polynomial preconditioner -- the default for every k in 1..4;
+//     cooperative grid (one CTA per SM), one CTA for tiny meshes, or (opt-in) one thread-block cluster;
+//   * classic (ls_pcg_persistent.cuh): round 1's three-synchronisation persistent kernel (LS_PCG_ALGO=classic, A/B and fallback);
 //   * graph (this file): one iteration = three kernels, a CUDA graph of CHUNK iterations replayed until a device-side
-//     `done` flag is seen -- the general fallback (K != 3, no cooperative launch) and the warm-start initialiser:
+//     `done` flag is seen -- the fallback when no cooperative launch is possible:
 //       K1  Ap = A p, pAp_k = p_k.Ap_k                     (SELL-32 or TMA-staged CSR SpMM + deterministic grid reduction)
 //       K2  x += a p; r -= a Ap; rz' = r.(dinv r); rr = r.r (fused update + 2K dot products; last CTA does the
 //           scalar state transition: beta, convergence per column, iteration count, done flag)
@@ -83,7 +86,7 @@ struct PcgHandle {
     int nslices;
     int sell_on;
     int sell_grid;
-    // pattern-only copy for matrices with one common off-diagonal value (ls_sell_kernel.cuh "PAT"; opt-in LS_PCG_PATTERN=1)
+    // pattern-only copy for matrices with one common off-diagonal value (ls_sell_kernel.cuh "PAT"; LS_PCG_PATTERN=0 switches it off)
     int *poff;
     int2 *pcol;
     float *diagp;

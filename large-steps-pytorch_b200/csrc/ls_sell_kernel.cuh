@@ -401,7 +401,7 @@ static __global__ void sell_fill_kernel(int V, int nslices, const int *__restric
 // Layout: slice s holds 32 * w2 int2 "pairs" at pc[poff[s] ...], pair (m, lane) = slots 2m and 2m+1 of row 32 s + lane, one
 // 8-byte load per lane per pair.  Unused slots point at the row itself and are paid back in the diagonal:
 // d'_i = M_ii - c * (unused slots of row i), so the inner loop has no per-lane predicate.
-// Opt-in for now (LS_PCG_PATTERN=1); detection is exact (bitwise equality of all off-diagonal values).
+// On by default since round 2 (LS_PCG_PATTERN=0 keeps the general copy); detection is exact (bitwise equality of all off-diagonal values).
 static __global__ void pat_detect_kernel(int V, const int *__restrict__ rowptr, const int *__restrict__ col,
                                          const float *__restrict__ val, unsigned int *__restrict__ mm /* [min, max] */) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
