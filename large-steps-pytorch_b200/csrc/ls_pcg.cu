@@ -33,6 +33,7 @@
 #include "ls_sell_kernel.cuh"
 #include "ls_pcg_persistent.cuh"
 #include "ls_pcg_fused.cuh"
+#include "ls_fused_inst.h"
 
 namespace {
 
@@ -886,45 +887,12 @@ int solve_persistent(PcgHandle *h, const float *b, float *x, float rtol, int max
 
 // ---- fused two-synchronisation solver (ls_pcg_fused.cuh) ------------------------------------------------------------
 // instantiation table: (K, RES, NW, PAT, SYNC, PROF) -> kernel, or NULL when that combination is not built
-template <int K, int RES, int NW, bool PAT, int SYNC, bool PROF, bool CHEB = false>
-const void *ffn() { return (const void *)lsf::pcg_fused_kernel<K, RES, NW, PAT, SYNC, PROF, CHEB>; }
-
+// instantiation table: (K, RES, NW, PAT, SYNC, PROF, CHEB) -> kernel, or NULL when that combination is not built.  The
+// instantiations live in three translation units (ls_fused_a/b/c.cu) so that they compile in parallel.
 const void *fused_fn(int K, int res, int nw, int pat, int sync, int prof, int cheb = 0) {
-    constexpr int W = lsp::PWARPS, WS = lsp::PT_SMALL / 32;
-    if (cheb) {   // Chebyshev preconditioner instantiations
-        if (K != 3 || prof) return nullptr;
-        if (sync == 0 && nw == W) {
-            if (res == 0) return pat ? ffn<3, 0, W, true, 0, false, true>() : ffn<3, 0, W, false, 0, false, true>();
-            if (res == 1) return pat ? ffn<3, 1, W, true, 0, false, true>() : ffn<3, 1, W, false, 0, false, true>();
-            if (res == 2) return pat ? ffn<3, 2, W, true, 0, false, true>() : ffn<3, 2, W, false, 0, false, true>();
-        }
-        if (sync == 0 && nw == WS && res == 2) return pat ? ffn<3, 2, WS, true, 0, false, true>() : ffn<3, 2, WS, false, 0, false, true>();
-        if (sync == 1 && nw == W && res == 2) return pat ? ffn<3, 2, W, true, 1, false, true>() : ffn<3, 2, W, false, 1, false, true>();
-        return nullptr;
-    }
-    if (K == 3 && !prof) {
-        if (sync == 0 && nw == W) {
-            if (res == 0) return pat ? ffn<3, 0, W, true, 0, false>() : ffn<3, 0, W, false, 0, false>();
-            if (res == 1) return pat ? ffn<3, 1, W, true, 0, false>() : ffn<3, 1, W, false, 0, false>();
-            if (res == 2) return pat ? ffn<3, 2, W, true, 0, false>() : ffn<3, 2, W, false, 0, false>();
-        }
-        if (sync == 0 && nw == WS && res == 2) return pat ? ffn<3, 2, WS, true, 0, false>() : ffn<3, 2, WS, false, 0, false>();
-        if (sync == 1 && nw == W && res == 2) return pat ? ffn<3, 2, W, true, 1, false>() : ffn<3, 2, W, false, 1, false>();
-        if (sync == 1 && nw == W && res == 3) return pat ? ffn<3, 3, W, true, 1, false>() : ffn<3, 3, W, false, 1, false>();
-    }
-    if (K == 3 && prof && nw == W) {
-        if (sync == 0 && res == 1) return pat ? ffn<3, 1, W, true, 0, true>() : ffn<3, 1, W, false, 0, true>();
-        if (sync == 0 && res == 2) return pat ? ffn<3, 2, W, true, 0, true>() : ffn<3, 2, W, false, 0, true>();
-        if (sync == 1 && res == 2) return pat ? ffn<3, 2, W, true, 1, true>() : ffn<3, 2, W, false, 1, true>();
-        if (sync == 1 && res == 3) return pat ? ffn<3, 3, W, true, 1, true>() : ffn<3, 3, W, false, 1, true>();
-    }
-    if (K == 4 && !prof && !pat && nw == W) {
-        if (sync == 0 && res == 0) return ffn<4, 0, W, false, 0, false>();
-        if (sync == 0 && res == 1) return ffn<4, 1, W, false, 0, false>();
-        if (sync == 0 && res == 2) return ffn<4, 2, W, false, 0, false>();
-        if (sync == 1 && res == 2) return ffn<4, 2, W, false, 1, false>();
-    }
-    return nullptr;
+    if (cheb) return (K == 3 && !prof) ? ls_fused_fn_cheb(res, nw, pat, sync) : nullptr;
+    if (K == 3 && !prof) return ls_fused_fn_jacobi(res, nw, pat, sync);
+    return ls_fused_fn_misc(K, res, nw, pat, sync, prof);
 }
 
 static int env_int(const char *name, int dflt) {

@@ -73,6 +73,31 @@ def test_host_side_argument_validation():
     assert lib.ls_launch_count() >= 0
 
 
+def test_round2_entry_points_validate_on_the_host():
+    lib = N.lib()
+    nb = ctypes.c_size_t(0)
+    assert lib.ls_glue_scratch_bytes(ctypes.byref(nb)) == N.LS_OK and nb.value >= 3 * 148 * 8
+    assert lib.ls_bucket_workspace_bytes(1000, ctypes.byref(nb)) == N.LS_OK and nb.value > 8000
+    assert lib.ls_bucket_workspace_bytes(-1, ctypes.byref(nb)) == N.LS_ERR_BAD_ARG
+    assert lib.ls_pcg_set_refinement(None, 1, 3.0) == N.LS_ERR_BAD_ARG and "handle" in N.last_error()
+    # the workspace size is a function of (V, nnz, k_max) only: no environment variable may change it
+    import os
+    sizes = []
+    for env in ({}, {"LS_PCG_PATTERN": "0"}, {"LS_PCG_PATTERN": "1", "LS_PCG_ALGO": "classic"}):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            assert lib.ls_pcg_workspace_bytes(250000, 1746002, 4, ctypes.byref(nb)) == N.LS_OK
+            sizes.append(nb.value)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    assert len(set(sizes)) == 1
+
+
 def test_check_maps_status_to_exceptions():
     with pytest.raises(IndexError):
         N.check(N.LS_ERR_INDEX_RANGE)
