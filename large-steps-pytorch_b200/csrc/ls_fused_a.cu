@@ -3,8 +3,15 @@
 #include "ls_fused_inst.h"
 
 namespace {
+#ifndef LS_ZH
+#define LS_ZH 1   // publish the preconditioned residual as bf16 rows (ls_pcg_fused.cuh "ZH"); -DLS_ZH=0 builds the fp32-row variant for A/B
+#endif
+// ZH applies to the 3-column Jacobi instantiations that publish through global memory
 template <int K, int RES, int NW, bool PAT, int SYNC, bool PROF, bool CHEB = false>
-const void *ffn() { return (const void *)lsf::pcg_fused_kernel<K, RES, NW, PAT, SYNC, PROF, CHEB>; }
+const void *ffn() {
+    constexpr bool ZH = (LS_ZH != 0) && K == 3 && !CHEB && RES != 3;
+    return (const void *)lsf::pcg_fused_kernel<K, RES, NW, PAT, SYNC, PROF, CHEB, ZH>;
+}
 constexpr int W = lsp::PWARPS, WS = lsp::PT_SMALL / 32;
 }  // namespace
 

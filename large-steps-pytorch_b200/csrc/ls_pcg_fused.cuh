@@ -28,6 +28,7 @@
 // SYNC = 1 one thread-block cluster (<= 16 CTAs: partials exchanged through distributed shared memory + barrier.cluster),
 // for meshes small enough that 16 SMs hold them -- a cluster barrier costs ~0.4 k cycles instead of ~4 k.
 #pragma once
+#include <cuda_bf16.h>
 #include "ls_pcg_persistent.cuh"
 
 namespace lsf {
@@ -53,7 +54,7 @@ struct FusedArgs {
     float *r;               // K planes                  (RES = 0)
     float *s;               // K planes                  (RES = 0)
     float *z;               // published rows of 4 floats
-    float *z2;              // second row buffer (Chebyshev steps ping-pong between the two)
+    float *z2;              // second row buffer (Chebyshev steps ping-pong between the two; ZH: holds the bf16 rows, 8 bytes each)
     float *cy, *cd;         // Chebyshev iterate and direction, K planes each (owner-only)
     int dp_smem;            // pattern copy: corrected diagonal kept in shared memory (when it fits)
     int cheb_m;             // polynomial degree + 1 (<= 1: plain Jacobi);  z = q(D^-1 A) D^-1 r with m - 1 extra SpMVs
@@ -278,6 +279,26 @@ __device__ __forceinline__ int2 ld_ent(const int2 *p) {
     return lsk::ld_entry(p);
 }
 
+// ---- the published preconditioned residual in bfloat16 (template flag ZH) ----------------------------------------------------
+// z = D^-1 r is the one vector every CTA gathers (6-7 times per row) and stores each iteration.  CG does not need it exactly: if
+// the SAME rounded vector z~ is used for the SpMV, for p = z~ + beta p and for gamma = r.z~, the recurrences s = A p, r = b - A x
+// stay exact and only the preconditioner is perturbed by <= 2^-9 relative -- iteration counts and final accuracy are unchanged
+// (numpy model and GPU tests: 99 / 124 / 537 -> 99 / 124 / 541 iterations, errors equal or smaller).  Rows of 4 x bf16 = 8 bytes
+// halve the store and gather traffic of the published vector.  Anything that needs full precision (the x rows of the
+// true-residual pass, the Chebyshev iterates) keeps using the fp32 row buffer.
+__device__ __forceinline__ uint2 pack_bf16_row(float a, float b, float c) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, 0.f);
+    return make_uint2(*reinterpret_cast<const unsigned int *>(&lo), *reinterpret_cast<const unsigned int *>(&hi));
+}
+__device__ __forceinline__ float4 unpack_bf16_row(const uint2 w) {
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16), 0.f);
+}
+__device__ __forceinline__ uint2 ld_coherent_u2(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
 constexpr size_t FUSED_SMEM_HDR = 4096 + 1024;   // reduction scratch + scalars, then the cluster exchange area
 __host__ __device__ inline size_t fused_off_bytes(int nsl_max) { return ((size_t)(2 * (nsl_max + 1)) * 4 + 127) / 128 * 128; }
 
@@ -290,9 +311,10 @@ inline size_t fused_smem_bytes(int K, int res, int nsl_max, int dp = 0, int cheb
     return FUSED_SMEM_HDR + 2 * NVMAX * 16 * 8 + fused_off_bytes(nsl_max) + (size_t)nsl_max * 32u * 4u * fused_row_floats(K, res, dp, cheb);
 }
 
-template <int K, int RES, int NW, bool PAT, int SYNC, bool PROF, bool CHEB = false>
+template <int K, int RES, int NW, bool PAT, int SYNC, bool PROF, bool CHEB = false, bool ZH = false>
 __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a) {
     static_assert(K == 3 || K == 4, "z rows are float4");
+    static_assert(!ZH || (K == 3 && !CHEB && RES != 3), "bf16 rows: 3 columns, Jacobi, published through global memory");
     constexpr bool KEEP = (SYNC == 1);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *red = reinterpret_cast<double *>(smem_raw);                       // NV*32 + NV doubles, NV <= 16  (<= 4224 B)
@@ -361,6 +383,25 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
         else *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row_) = v_;
     };
     const bool dp_smem = PAT && a.dp_smem != 0;
+    // the published PRECONDITIONED RESIDUAL (phase B -> phase A): bf16 rows when ZH, else the same fp32 rows as above
+    uint2 *zh = reinterpret_cast<uint2 *>(a.z2);
+    auto ZldP = [&](int col) -> float4 {
+        if constexpr (ZH) return unpack_bf16_row(ld_coherent_u2(zh + col));
+        else return Zld(col);
+    };
+    // rounds zz[] to what the other CTAs will see, stores the row; the caller keeps using the rounded zz[] (consistency)
+    auto ZstP = [&](int row_, float (&zz)[4]) {
+        if constexpr (ZH) {
+            const uint2 w = pack_bf16_row(zz[0], zz[1], zz[2]);
+            const float4 q = unpack_bf16_row(w);
+            zz[0] = q.x;
+            zz[1] = q.y;
+            zz[2] = q.z;
+            zh[row_] = w;
+        } else {
+            Zst(row_, make_float4(zz[0], zz[1], zz[2], zz[3]));
+        }
+    };
 
     long long tA = 0, tS2 = 0, tB = 0, tS1 = 0, tX = 0, t0 = 0;
     const bool prof = PROF && (a.dbg != nullptr) && tid == 0;
@@ -441,8 +482,8 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                     float4 xa[UB], xb[UB];
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
-                        xa[u] = Zld(cv[u].x);
-                        xb[u] = Zld(cv[u].y);
+                        xa[u] = ZldP(cv[u].x);
+                        xb[u] = ZldP(cv[u].y);
                     }
                     zo = own(li, row);
                     dp = dp_smem ? dp_s[(size_t)li * 32 + lane] : a.diagp[row];
@@ -471,8 +512,8 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                     float4 xa[U], xb[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        xa[u] = Zld(cv[u].x);
-                        xb[u] = Zld(cv[u].y);
+                        xa[u] = ZldP(cv[u].x);
+                        xb[u] = ZldP(cv[u].y);
                     }
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
@@ -494,7 +535,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 {
                     float4 xv[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) xv[u] = Zld(cv[u].x);
+                    for (int u = 0; u < U; ++u) xv[u] = ZldP(cv[u].x);
                     pre(li, row);
                     if (sn < s_end) {
                         const int n0 = off_s[li + NW], wn = (off_s[li + NW + 1] - n0) >> 5;
@@ -516,7 +557,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                     for (int u = 0; u < U; ++u) cv[u] = (j + u < w) ? ld_ent<KEEP>(e + (j + u) * 32) : make_int2(row, 0);
                     float4 xv[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) xv[u] = Zld(cv[u].x);
+                    for (int u = 0; u < U; ++u) xv[u] = ZldP(cv[u].x);
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const float wv = __int_as_float(cv[u].y);
@@ -539,9 +580,10 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
             else return Zld(row);
         } else if constexpr (RES >= 1) {
             const float di_ = Dv(li, row);
-            return make_float4(di_ * R(li, 0, row), di_ * R(li, 1, row), di_ * R(li, 2, row), K > 3 ? di_ * R(li, K > 3 ? 3 : 0, row) : 0.f);
+            if constexpr (ZH) return unpack_bf16_row(pack_bf16_row(di_ * R(li, 0, row), di_ * R(li, 1, row), di_ * R(li, 2, row)));
+            else return make_float4(di_ * R(li, 0, row), di_ * R(li, 1, row), di_ * R(li, 2, row), K > 3 ? di_ * R(li, K > 3 ? 3 : 0, row) : 0.f);
         } else {
-            return Zld(row);
+            return ZldP(row);
         }
     };
 
@@ -625,8 +667,10 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
             if (RES) d_s[(size_t)li * 32 + lane] = di;
             float zz[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
+            for (int k = 0; k < K; ++k) zz[k] = di * bv[k];
+            ZstP(row, zz);                 // (rounds zz to the published values when ZH)
+#pragma unroll
             for (int k = 0; k < K; ++k) {
-                zz[k] = di * bv[k];
                 R(li, k, row) = bv[k];
                 Sv(li, k, row) = 0.f;
                 X(li, k, row) = 0.f;
@@ -634,7 +678,6 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 acc[k] += (double)bv[k] * (double)zz[k];
                 acc[K + k] += (double)bv[k] * (double)bv[k];
             }
-            Zst(row, make_float4(zz[0], zz[1], zz[2], zz[3]));
         }
         if constexpr (CHEB) {
             if (cheb_m > 1) {     // gamma = r . q(D^-1 A) D^-1 r instead of r . D^-1 r
@@ -726,7 +769,8 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
             for (int k = 0; k < K; ++k) {
                 const float rv = (float)((double)bv[k] - ax[k]);
                 R(li, k, row) = rv;
-                const float zz = di * rv;
+                float zz = di * rv;
+                if constexpr (ZH) zz = __bfloat162float(__float2bfloat16_rn(zz));   // gamma = r . z~ with the z~ that gets published below
                 acc[k] += (double)rv * (double)zz;
                 acc[K + k] += (double)rv * (double)rv;
                 acc[2 * K + k] += (double)fl[k] * (double)fl[k];
@@ -798,7 +842,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                     }
                 }
                 if (cheb_m <= 1)      // (Chebyshev: the preconditioned residual is already published in zcur)
-                    Zst(row, make_float4(zz[0], zz[1], zz[2], zz[3]));
+                    ZstP(row, zz);
             }
             sync.barrier();
         }
@@ -907,17 +951,19 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 for (int s = s_begin + warp; s < s_end; s += NW) {
                     const int li = s - s_begin, row = s * 32 + lane;
                     const float di = Dv(li, row);
-                    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+                    float zz[4] = {0.f, 0.f, 0.f, 0.f}, rn[K];
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        const float rn = fmaf(-alpha[k], Sv(li, k, row), R(li, k, row));
-                        R(li, k, row) = rn;
-                        zz[k] = di * rn;
-                        const float r2 = rn * rn;
-                        acc2[k] += (double)(di * r2);
-                        acc2[K + k] += (double)r2;
+                        rn[k] = fmaf(-alpha[k], Sv(li, k, row), R(li, k, row));
+                        R(li, k, row) = rn[k];
+                        zz[k] = di * rn[k];
                     }
-                    Zst(row, make_float4(zz[0], zz[1], zz[2], zz[3]));
+                    ZstP(row, zz);             // (rounds zz to the published values when ZH)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        acc2[k] += (double)(rn[k] * zz[k]);
+                        acc2[K + k] += (double)(rn[k] * rn[k]);
+                    }
                 }
                 if (prof) { const long long t1 = clock64(); tB += t1 - t0; t0 = t1; }
                 auto postB = [&](const double gn, const double rrn) {   // beta, convergence, stop decision
