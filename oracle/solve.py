@@ -131,3 +131,65 @@ def jacobi_pcg_f32(rows, cols, vals, V, b, x0=None, rtol=1e-7, maxit=10000, prec
         active = active & (rr > (rtol * rtol) * bb)
     relres = np.sqrt(rr / np.where(bb == 0, 1, bb))
     return x, it, relres
+
+
+def _bf16(x):
+    """round-to-nearest-even to bfloat16, returned as float32 (what cvt.rn.bf16.f32 + a 16-bit shift give on the device)"""
+    u = np.ascontiguousarray(x, dtype=f32).view(np.uint32)
+    r = ((u >> 16) & 1) + 0x7fff
+    return ((u + r) & np.uint32(0xffff0000)).view(f32)
+
+
+def fused_pcg_f32(rows, cols, vals, V, b, rtol=1e-7, maxit=10000, bf16_rows=True, refine=1, theta=3.0):
+    """Model of ls_pcg_fused.cuh.  Per iteration:
+         phase B  r -= alpha s;  z = rnd(D^-1 r);  gamma' = r.z, rr = r.r        -> reduction 1 (beta, convergence)
+         phase A  w = A z;  x += alpha_prev p;  p = z + beta p;  s = w + beta s;  delta = p.s   -> reduction 2 (alpha)
+       and at convergence the true residual b - A x (fp64) decides whether to restart.
+       Returns (x, iterations, restarts)."""
+    A = _csr(rows, cols, vals, V, f32)
+    A64, Aabs = A.astype(np.float64), abs(A.astype(np.float64))
+    b = np.asarray(b, dtype=f32)
+    dinv = (f32(1.0) / A.diagonal().astype(f32))
+    d = lambda u, w: np.einsum("ij,ij->j", u.astype(np.float64), w.astype(np.float64))
+    rnd = _bf16 if bf16_rows else (lambda t: t)
+    bb = d(b, b)
+    x = np.zeros_like(b)
+    r = b.copy()
+    active = bb > 0
+    it = restarts = checks = 0
+    while True:
+        z = rnd((dinv[:, None] * r).astype(f32))
+        gam = d(r, z)
+        p = np.zeros_like(b)
+        s = np.zeros_like(b)
+        alpha = np.zeros(b.shape[1], dtype=f32)
+        beta = np.zeros(b.shape[1], dtype=f32)
+        while active.any() and it < maxit:
+            w = (A @ z).astype(f32)                                   # phase A
+            x = (x + alpha[None, :] * p).astype(f32)
+            p = (z + beta[None, :] * p).astype(f32)
+            s = (w + beta[None, :] * s).astype(f32)
+            dl = d(p, s)
+            alpha = np.where(active & (dl > 0), gam / np.where(dl == 0, 1, dl), 0.0).astype(f32)
+            r = (r - alpha[None, :] * s).astype(f32)                   # phase B
+            z = rnd((dinv[:, None] * r).astype(f32))
+            gam_new, rr = d(r, z), d(r, r)
+            it += 1
+            conv = rr <= (rtol * rtol) * bb
+            beta = np.where(active & ~conv, gam_new / np.where(gam == 0, 1, gam), 0.0).astype(f32)
+            gam = gam_new
+            active = active & ~conv
+        x = (x + alpha[None, :] * p).astype(f32)                      # pending update
+        if refine <= 0 or checks > refine or it == 0 or it >= maxit:
+            break
+        rt = b.astype(np.float64) - A64 @ x.astype(np.float64)
+        floor = Aabs @ np.abs(x.astype(np.float64))
+        rrt, fl2 = d(rt, rt), d(floor, floor)
+        checks += 1
+        need = (rrt > (rtol * rtol) * bb) & (rrt > (theta * 2.0 ** -24) ** 2 * fl2) & (bb > 0) & (restarts < refine)
+        if not need.any():
+            break
+        restarts += 1
+        r = rt.astype(f32)
+        active = need
+    return x, it, restarts

@@ -226,3 +226,32 @@ def test_pattern_layout_model(bunny_mesh):
     assert err < 5e-7 and max(widths) > 2 * U
     err, widths = run(*workloads.plane(12), 5.0)
     assert err < 5e-7 and min(widths) <= 3           # exercises the 3-pair body and its pay-back
+
+
+def test_meshops_and_remesh_reject_cpu_tensors_and_bad_arguments():
+    """No CPU fallback anywhere: the loop glue and the re-parameteriser raise on CPU tensors, like every other operator."""
+    import pytest
+    import torch
+    from largesteps_b200 import meshops
+    from largesteps_b200.remesh import Reparameterizer, Arena
+    v = torch.rand(5, 3)
+    f = torch.tensor([[0, 1, 2], [2, 3, 4]])
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        meshops.compute_face_normals(v, f)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        meshops.compute_vertex_normals(v, f, torch.zeros(3, 2))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        meshops.gather_rows(v, torch.tensor([0, 1]))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        Reparameterizer(lambda_=19.0).update(v, f)
+    with pytest.raises(ValueError, match="Unknown solver type"):
+        Reparameterizer(method="QR")
+    # setup-time helpers are plain torch and keep the reference's semantics (scripts/geometry.py:3-35)
+    vd = torch.tensor([[0., 0, 0], [1, 0, 0], [0, 1, 0], [1, 0, 0]])
+    fd = torch.tensor([[0, 1, 2], [0, 2, 3]])
+    vu, fu, inv = meshops.remove_duplicates(vd, fd)
+    assert vu.shape == (3, 3) and torch.equal(vu[inv], vd) and torch.equal(vu[fu], vd[fd])
+    assert abs(float(meshops.average_edge_length(vd, fd)) - (2 + 2 ** 0.5) / 3) < 1e-6
+    a = Arena()
+    with pytest.raises(MemoryError):
+        a.take(16, torch.device("cpu"))
