@@ -31,6 +31,10 @@
 #include <cuda_bf16.h>
 #include "ls_pcg_persistent.cuh"
 
+#ifndef LS_POLL_FENCE
+#define LS_POLL_FENCE 0   // A/B (build_variant.sh pollfence -DLS_POLL_FENCE=1)
+#endif
+
 namespace lsf {
 
 using lsp::GridBar;
@@ -147,9 +151,18 @@ struct GridSync {
                         // release: the z rows every thread of this CTA stored before the CTA barrier above are visible to
                         // whoever acquires this word; the acquire below invalidates L1 so the gathers that follow miss it
                         asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(slot + lane), "l"(word) : "memory");
+#if LS_POLL_FENCE
+                        // poll with relaxed loads, acquire once at the end (MEMBAR.ALL.GPU + one CCTL.IVALL) instead of an
+                        // acquire load -- and its L1 invalidate -- per polling round trip
+                        do {
+                            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(slot + lane) : "memory");
+                        } while ((int)(w & 0xffull) != G);
+                        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#else
                         do {
                             w = ld_acquire64(slot + lane);
                         } while ((int)(w & 0xffull) != G);
+#endif
                     } else {
                         atomicAdd(slot + lane, word);
                         do {
