@@ -288,10 +288,9 @@ def run_b200(args, wl, wl_name):
         ms = e0.elapsed_time(e1)
         return D.max_over_ranks(ms, device=dev), N.launch_count() - n0
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
+    sampler = ClockSampler(local)       # every rank watches its own GPU (per-rank clock skew was unobserved)
+    sampler.start()
+    time.sleep(0.3)
 
     # ---- value: device-resident right-hand sides ---------------------------------------------------------
     iters = []
@@ -580,7 +579,20 @@ def run_b200(args, wl, wl_name):
                                                   "what": "Reparameterizer.update (assembly + to_differential + solver build) + first from_differential, wall clock"}
             del rp, Mx, ux
 
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    if world > 1:
+        import torch.distributed as tdist
+        allc = [None] * world
+        tdist.all_gather_object(allc, clocks)            # outside every timed region
+        if rank == 0:
+            meds = [c["sm_mhz"] for c in allc if c and c.get("sm_mhz") is not None]
+            clocks = {"sm_mhz": min(meds) if meds else None,
+                      "sm_max_mhz": max([c["sm_max_mhz"] for c in allc if c and c.get("sm_max_mhz")] or [None]),
+                      "reasons": sorted(set(r for c in allc if c for r in c.get("reasons", []))),
+                      "samples": sum(c.get("samples", 0) for c in allc if c),
+                      "what": "sm_mhz = lowest per-rank median under load; reasons = union over ranks",
+                      "per_rank": [{"rank": i, "sm_mhz": c.get("sm_mhz"), "reasons": c.get("reasons"),
+                                    "power_w_max": c.get("power_w_max")} for i, c in enumerate(allc) if c]}
 
     # ---- trivial gather (the only collective): checksum of every rank's last solution ---------------------
     with torch.no_grad():
