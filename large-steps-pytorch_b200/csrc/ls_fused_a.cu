@@ -24,5 +24,8 @@ const void *ls_fused_fn_jacobi(int res, int nw, int pat, int sync) {
     if (sync == 0 && nw == WS && res == 2) return pat ? ffn<3, 2, WS, true, 0, false>() : ffn<3, 2, WS, false, 0, false>();
     if (sync == 1 && nw == W && res == 2) return pat ? ffn<3, 2, W, true, 1, false>() : ffn<3, 2, W, false, 1, false>();
     if (sync == 1 && nw == W && res == 3) return pat ? ffn<3, 3, W, true, 1, false>() : ffn<3, 3, W, false, 1, false>();
+    // one cluster, published rows in distributed shared memory (meshes of a few thousand vertices)
+    if (sync == 1 && nw == W && res == 4) return pat ? ffn<3, 4, W, true, 1, false>() : ffn<3, 4, W, false, 1, false>();
+    if (sync == 1 && nw == WS && res == 4) return pat ? ffn<3, 4, WS, true, 1, false>() : ffn<3, 4, WS, false, 1, false>();
     return nullptr;
 }

@@ -21,12 +21,15 @@ const void *ls_fused_fn_misc(int K, int res, int nw, int pat, int sync, int prof
         if (sync == 0 && res == 2) return pat ? ffn<3, 2, W, true, 0, true>() : ffn<3, 2, W, false, 0, true>();
         if (sync == 1 && res == 2) return pat ? ffn<3, 2, W, true, 1, true>() : ffn<3, 2, W, false, 1, true>();
         if (sync == 1 && res == 3) return pat ? ffn<3, 3, W, true, 1, true>() : ffn<3, 3, W, false, 1, true>();
+        if (sync == 1 && res == 4) return pat ? ffn<3, 4, W, true, 1, true>() : ffn<3, 4, W, false, 1, true>();
     }
+    if (K == 3 && prof && nw == WS && sync == 1 && res == 4) return pat ? ffn<3, 4, WS, true, 1, true>() : ffn<3, 4, WS, false, 1, true>();
     if (K == 4 && !prof && !pat && nw == W) {
         if (sync == 0 && res == 0) return ffn<4, 0, W, false, 0, false>();
         if (sync == 0 && res == 1) return ffn<4, 1, W, false, 0, false>();
         if (sync == 0 && res == 2) return ffn<4, 2, W, false, 0, false>();
         if (sync == 1 && res == 2) return ffn<4, 2, W, false, 1, false>();
+        if (sync == 1 && res == 4) return ffn<4, 4, W, false, 1, false>();
     }
     return nullptr;
 }

@@ -35,6 +35,10 @@
 #include "ls_pcg_fused.cuh"
 #include "ls_fused_inst.h"
 
+#ifndef LS_CLRES_DEFAULT
+#define LS_CLRES_DEFAULT 0     // slices (x 32 vertices); 0 = off: measured slower than the cooperative grid, see clres_limit()
+#endif
+
 namespace {
 
 constexpr int KMAX = 4;
@@ -900,6 +904,21 @@ static int env_int(const char *name, int dflt) {
     return (e && e[0]) ? atoi(e) : dflt;
 }
 
+// LS_PCG_CLRES=N (opt-in): meshes of (one CTA's worth) < slices <= N run as ONE cluster of 16 CTAs with every vector -- the
+// published rows included -- in (distributed) shared memory: RES = 4 of ls_pcg_fused.cuh; inside the iteration nothing but matrix
+// entries comes from global memory.  Built because a 2.5 K-vertex solve "should not touch global memory"  -- and
+// measured slower than the cooperative grid with the Chebyshev steps (profiles/r02_cluster_resident.jsonl): icosphere 0.278 vs
+// 0.233 ms, 10 K vertices 0.47 vs 0.24 ms.  Per iteration (CTA 0, 2562 vertices): gather pass 2.3 k cycles (14 remote 8-byte
+// loads per row against ~20 B/clk of DSMEM bandwidth per SM), the two exchanges 2.3 k + 3.4 k (fp64 shuffle trees, 16 remote
+// stores, barrier.cluster with release/acquire, fixed-order re-sum, fp64 division) -- a cluster synchronisation that carries a
+// deterministic reduction is ~2 k cycles, not the 0.4 k of a bare barrier.cluster, and 16 SMs are 16 SMs.
+constexpr int CLRES_CS = 16;
+static int clres_limit() { return env_int("LS_PCG_CLRES", LS_CLRES_DEFAULT); }
+static bool clres_regime(int nslices) {
+    if (env_int("LS_PCG_CLUSTER", -1) == 0) return false;
+    return nslices > env_int("LS_PCG_ONECTA", lsp::PWARPS) && nslices <= clres_limit();
+}
+
 // Choose grid / cluster, residency and CTA shape for one K.  Small meshes (the CTA-resident rows of <= 16 SMs hold them)
 // run as ONE thread-block cluster; everything else as a cooperative grid with one CTA per SM.
 int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCfg *c) {
@@ -919,6 +938,7 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
         return n;
     };
     const int cap3 = cap_slices(3, pat), cap2 = cap_slices(2, 0), cap1 = cap_slices(1, 0);
+    const int cap4 = cheb ? 0 : (cap_slices(4, 0) < 63 ? cap_slices(4, 0) : 63);   // (63: the owner of a row is found by a 16-bit multiply)
     const int want_cluster = env_int("LS_PCG_CLUSTER", -1);   // -1 auto, 0 never, N force cluster size N
     const int force_res = env_int("LS_PCG_RES", -1);
     // ---- one CTA (everything, including the gathered vector, in shared memory) or, on request, one cluster
@@ -929,14 +949,21 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
         // one CTA only while every warp has at most one slice: beyond that the single SM is instruction-issue bound (81 slices: 8.4 k
         // cycles for phase A alone) and the cooperative grid wins despite its ~2 x 3.5 k cycles of synchronisation per iteration
         if (h->nslices <= env_int("LS_PCG_ONECTA", W)) cs = 1;
+        else if (!cheb && clres_regime(h->nslices)) cs = CLRES_CS;
         if (want_cluster > 0) cs = want_cluster;
         if (cs > 0 && (h->nslices + cs - 1) / cs > cap2) cs = 0;
     }
     if (cs > 0) {
         const int nsl_max = (h->nslices + cs - 1) / cs;
         int res = (cs == 1 && K == 3 && h->cheb_m <= 1 && nsl_max <= cap3 && !(force_res >= 0 && force_res < 3)) ? 3 : 2;
+        int nwc = W;
+        if (cs > 1 && !cheb && nsl_max <= cap4 && !(force_res >= 0 && force_res < 4)) {
+            res = 4;
+            if (K == 3 && nsl_max <= lsp::PT_SMALL / 32 && !(getenv("LS_PCG_SMALLCTA") && getenv("LS_PCG_SMALLCTA")[0] == '0')) nwc = lsp::PT_SMALL / 32;
+        }
+        if (res == 4 && !fused_fn(K, res, nwc, pat, 1, 0, cheb)) { res = 2; nwc = W; }
         const int dp = (pat && nsl_max <= cap_slices(res, 1)) ? 1 : 0;
-        const void *fn = fused_fn(K, res, W, pat, 1, 0, cheb);
+        const void *fn = fused_fn(K, res, nwc, pat, 1, 0, cheb);
         const size_t smem = lsf::fused_smem_bytes(K, res, nsl_max, dp, cheb);
         bool ok = fn != nullptr;
         if (ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin) != cudaSuccess) ok = false;
@@ -944,7 +971,7 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
         if (ok && cs > 1) {
             cudaLaunchConfig_t lc = {};
             lc.gridDim = dim3(cs);
-            lc.blockDim = dim3(W * 32);
+            lc.blockDim = dim3(nwc * 32);
             lc.dynamicSmemBytes = smem;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
@@ -957,8 +984,8 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
             if (cudaOccupancyMaxActiveClusters(&ncl, fn, &lc) != cudaSuccess || ncl < 1) ok = false;
         }
         if (ok) {
-            c->on = 1; c->grid = cs; c->res = res; c->nw = W; c->sync = 1; c->cluster = cs; c->nsl_max = nsl_max; c->pat = pat; c->dp = dp;
-            c->smem = smem; c->fn = fn; c->fn_prof = cheb ? nullptr : fused_fn(K, res, W, pat, 1, 1);
+            c->on = 1; c->grid = cs; c->res = res; c->nw = nwc; c->sync = 1; c->cluster = cs; c->nsl_max = nsl_max; c->pat = pat; c->dp = dp;
+            c->smem = smem; c->fn = fn; c->fn_prof = cheb ? nullptr : fused_fn(K, res, nwc, pat, 1, 1);
             if (c->fn_prof) {
                 cudaFuncSetAttribute(c->fn_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin);
                 if (cs > 8) cudaFuncSetAttribute(c->fn_prof, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -1345,6 +1372,9 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
         const int nsl_max = (h->nslices + g - 1) / g;
         const bool fits = lsf::fused_smem_bytes(3, 2, nsl_max, 1, 1) <= (size_t)di.max_smem_optin;
         precond = (h->nslices > env_int("LS_PCG_ONECTA", lsp::PWARPS) && fits) ? 2 : 1;
+        // ... and not where one cluster holds everything in shared memory: a synchronisation costs a tenth there, plain CG's
+        // fewer SpMVs win
+        if (clres_regime(h->nslices)) precond = 1;
         h->precond = precond;
     }
     if (precond == 2) {

@@ -24,6 +24,9 @@
 // Data placement (per row, K = 3): r, s, D^-1 in shared memory (RES >= 1: 28 B/row), additionally x and the owner's p
 // (RES = 2: 52 B/row, mid-size meshes); z rows (16 B) and, below RES = 2, x / p planes in global memory (L2-resident).
 // Slice offsets of the CTA's own slices are copied to shared memory once.
+// RES = 4 (one cluster, meshes of a few thousand vertices): every vector in shared memory INCLUDING the published rows, which the
+// other CTAs of the cluster gather through distributed shared memory (mapa + ld.shared::cluster) -- inside the iteration nothing
+// but the (read-only) matrix entries comes from global memory and a synchronisation is one barrier.cluster.
 // Synchronisation: SYNC = 0 the whole grid (fixed-point single-atomic all-reduce, release/acquire where it publishes z),
 // SYNC = 1 one thread-block cluster (<= 16 CTAs: partials exchanged through distributed shared memory + barrier.cluster),
 // for meshes small enough that 16 SMs hold them -- a cluster barrier costs ~0.4 k cycles instead of ~4 k.
@@ -315,7 +318,7 @@ __device__ __forceinline__ uint2 ld_coherent_u2(const uint2 *p) {
 constexpr size_t FUSED_SMEM_HDR = 4096 + 1024;   // reduction scratch + scalars, then the cluster exchange area
 __host__ __device__ inline size_t fused_off_bytes(int nsl_max) { return ((size_t)(2 * (nsl_max + 1)) * 4 + 127) / 128 * 128; }
 
-// floats per row kept in shared memory: RES 1: r, s, D^-1;  RES 2: + x, p;  RES 3 (single CTA): + the z rows (4 floats);
+// floats per row kept in shared memory: RES 1: r, s, D^-1;  RES 2: + x, p;  RES 3 (single CTA) and 4 (cluster): + the z rows (4 floats);
 // dp: + the pattern copy's corrected diagonal;  cheb (RES 2): + the Chebyshev iterate and direction
 __host__ __device__ inline int fused_row_floats(int K, int res, int dp, int cheb = 0) {
     return (res == 0 ? 0 : (res == 1 ? 2 * K + 1 : (res == 2 ? 4 * K + 1 : 4 * K + 5))) + (dp ? 1 : 0) + ((cheb && res == 2) ? 2 * K : 0);
@@ -327,7 +330,8 @@ inline size_t fused_smem_bytes(int K, int res, int nsl_max, int dp = 0, int cheb
 template <int K, int RES, int NW, bool PAT, int SYNC, bool PROF, bool CHEB = false, bool ZH = false>
 __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a) {
     static_assert(K == 3 || K == 4, "z rows are float4");
-    static_assert(!ZH || (K == 3 && !CHEB && RES != 3), "bf16 rows: 3 columns, Jacobi, published through global memory");
+    static_assert(!ZH || (K == 3 && !CHEB && RES != 3), "bf16 rows: 3 columns, Jacobi, published through global or distributed shared memory");
+    static_assert(RES != 4 || (SYNC == 1 && !CHEB), "cluster-resident rows: one cluster, Jacobi");
     constexpr bool KEEP = (SYNC == 1);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *red = reinterpret_cast<double *>(smem_raw);                       // NV*32 + NV doubles, NV <= 16  (<= 4224 B)
@@ -343,14 +347,15 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
     float *x_s = d_s + (size_t)(RES >= 1 ? nsl_max : 0) * 32;                 // RES >= 2
     float *p_s = x_s + (size_t)nsl_max * K * 32;
     float *z_s = p_s + (size_t)nsl_max * K * 32;                              // RES = 3: rows of 4 floats, the "published" vector never leaves the SM
-    float *dp_s = (RES == 3 ? z_s + (size_t)nsl_max * 128 : (RES == 2 ? z_s : (RES == 1 ? x_s : fs)));   // optional [nsl_max][32]
+    float *dp_s = (RES >= 3 ? z_s + (size_t)nsl_max * 128 : (RES == 2 ? z_s : (RES == 1 ? x_s : fs)));   // optional [nsl_max][32]
     float *cy_s = dp_s + (size_t)((PAT && a.dp_smem) ? nsl_max : 0) * 32;     // CHEB && RES == 2: [nsl_max][K][32] each
     float *cd_s = cy_s + (size_t)nsl_max * K * 32;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
-    const int s_begin = (int)((long long)a.nslices * cta / G);
-    const int s_end = (int)((long long)a.nslices * (cta + 1) / G);
+    // RES = 4: uniform blocks of nsl_max slices, so that the owner of a gathered row is a division by a constant
+    const int s_begin = (RES == 4) ? min(cta * nsl_max, a.nslices) : (int)((long long)a.nslices * cta / G);
+    const int s_end = (RES == 4) ? min(s_begin + nsl_max, a.nslices) : (int)((long long)a.nslices * (cta + 1) / G);
     const long long Vp = a.Vp;
     const int kb = a.kb;
     constexpr int U = PAT ? 4 : 8;
@@ -387,19 +392,41 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
     float *zcur = a.z, *zalt = a.z2;   // the published vector lives in zcur; Chebyshev steps write the next iterate to zalt and swap
     const int cheb_m = CHEB ? a.cheb_m : 0;   // the polynomial preconditioner is compiled into its own instantiations only
     // the published rows: global memory, or (RES = 3, one CTA owns every row) shared memory
+    // RES = 4: row `col` lives in the shared memory of CTA (col / 32) / nsl_max of the cluster, at the same offset in every CTA.
+    // The division is a multiplication: exact for slice < 16 nsl_max when nsl_max < 64 (s e < 2^16 with e = M nsl_max - 2^16 <= nsl_max).
+    const unsigned int dsm_base = ls_smem_u32(z_s);
+    const unsigned int dsm_magic = 65536u / (unsigned int)max(nsl_max, 1) + 1u;
+    const unsigned int dsm_rows = (unsigned int)nsl_max * 32u;
+    auto dsm_addr = [&](int col, unsigned int rowbytes) -> unsigned int {
+        const unsigned int own = (((unsigned int)col >> 5) * dsm_magic) >> 16;
+        const unsigned int lr = (unsigned int)col - own * dsm_rows;
+        unsigned int ra;
+        asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(dsm_base + lr * rowbytes), "r"(own));
+        return ra;
+    };
     auto Zld = [&](int col) -> float4 {
         if constexpr (RES == 3) return *reinterpret_cast<const float4 *>(z_s + 4 * (size_t)col);
-        else return lsp::ld_coherent4(zcur + 4 * (size_t)col);
+        else if constexpr (RES == 4) {
+            float4 v;
+            asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(dsm_addr(col, 16u)) : "memory");
+            return v;
+        } else return lsp::ld_coherent4(zcur + 4 * (size_t)col);
     };
     auto Zst = [&](int row_, const float4 v_) {
         if constexpr (RES == 3) *reinterpret_cast<float4 *>(z_s + 4 * (size_t)row_) = v_;
+        else if constexpr (RES == 4) *reinterpret_cast<float4 *>(z_s + 4 * (size_t)(row_ - s_begin * 32)) = v_;
         else *reinterpret_cast<float4 *>(zcur + 4 * (size_t)row_) = v_;
     };
     const bool dp_smem = PAT && a.dp_smem != 0;
     // the published PRECONDITIONED RESIDUAL (phase B -> phase A): bf16 rows when ZH, else the same fp32 rows as above
-    uint2 *zh = reinterpret_cast<uint2 *>(a.z2);
+    // (RES = 4: the bf16 rows alias the fp32 row area -- the two uses are always separated by a cluster barrier)
+    uint2 *zh = (RES == 4) ? reinterpret_cast<uint2 *>(z_s) - (size_t)s_begin * 32 : reinterpret_cast<uint2 *>(a.z2);
     auto ZldP = [&](int col) -> float4 {
-        if constexpr (ZH) return unpack_bf16_row(ld_coherent_u2(zh + col));
+        if constexpr (ZH && RES == 4) {
+            uint2 w;
+            asm volatile("ld.shared::cluster.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(dsm_addr(col, 8u)) : "memory");
+            return unpack_bf16_row(w);
+        } else if constexpr (ZH) return unpack_bf16_row(ld_coherent_u2(zh + col));
         else return Zld(col);
     };
     // rounds zz[] to what the other CTAs will see, stores the row; the caller keeps using the rounded zz[] (consistency)

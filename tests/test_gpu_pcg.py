@@ -211,6 +211,10 @@ def test_morton_reorder_is_transparent(bunny_mesh):
 MODES = [
     {},                                                         # default: fused kernel on the cooperative grid (one CTA for tiny meshes), pattern copy if uniform
     {"LS_PCG_CLUSTER": "16"},                                   # one thread-block cluster of 16 CTAs (DSMEM all-reduce, barrier.cluster)
+    {"LS_PCG_CLUSTER": "16", "LS_PCG_RES": "2"},                # ... publishing through global memory (the cluster-resident rows switched off)
+    {"LS_PCG_CLRES": "384"},                                    # cluster-resident mode (opt-in): <= 12 K vertices in one cluster, rows gathered through DSMEM
+    {"LS_PCG_CLRES": "384", "LS_PCG_SMALLCTA": "0"},            # ... 768-thread CTAs
+    {"LS_PCG_CLRES": "384", "LS_PCG_PATTERN": "0"},             # ... general matrix copy
     {"LS_PCG_CLUSTER": "0"},                                    # fused, cooperative grid, everything in shared memory (256-thread CTAs)
     {"LS_PCG_CLUSTER": "0", "LS_PCG_SMALLCTA": "0"},            # ... 768-thread CTAs
     {"LS_PCG_CLUSTER": "0", "LS_PCG_RES": "1"},                 # ... x / p in global memory
@@ -265,6 +269,10 @@ def test_every_solver_mode_meets_the_bar(env, bunny_mesh, monkeypatch):
                     assert d["cluster"] == int(env["LS_PCG_CLUSTER"])
             elif tiny:
                 assert d["cluster"] == 1 and d["grid"] == 1 and d["residency"] == int(env.get("LS_PCG_RES", "3"))
+            elif V <= 32 * int(env.get("LS_PCG_CLRES", "0")):
+                # a few thousand vertices: one cluster of 16 CTAs, the published rows gathered through distributed shared memory
+                assert d["cluster"] == 16 and d["grid"] == 16 and d["residency"] == 4
+                assert d["threads"] == (256 if (V + 31) // 32 <= 16 * 8 and env.get("LS_PCG_SMALLCTA") != "0" else 768)
             else:
                 assert d["cluster"] == 0 and d["grid"] == min(148, (V + 31) // 32) and d["residency"] == 2
         if "LS_FORCE_REORDER" in env and V >= 8192:      # (smaller meshes carry no Morton order: everything is cache resident)
