@@ -34,6 +34,9 @@
 #include <cuda_bf16.h>
 #include "ls_pcg_persistent.cuh"
 
+#ifndef LS_RING_SOA
+#define LS_RING_SOA 0     // A/B (build_variant.sh ringsoa -DLS_RING_SOA=1)
+#endif
 #ifndef LS_POLL_FENCE
 #define LS_POLL_FENCE 0   // A/B (build_variant.sh pollfence -DLS_POLL_FENCE=1)
 #endif
@@ -124,7 +127,13 @@ struct GridSync {
         const int ns = S->nslot;
         bool ok = false;
         if (allow_fast && ns < ring_slots && G <= 255) {
+#if LS_RING_SOA
+            // word i of every slot lives in its own plane of ring_slots words: the NV words of one all-reduce sit in different
+            // L2 slices, so the G atomics (and the pollers) of each word do not queue behind the other words'
+            unsigned long long *slot = ring + (size_t)ns - (size_t)lane + (size_t)lane * (size_t)ring_slots;   // (used as slot + lane)
+#else
             unsigned long long *slot = ring + 8 * (size_t)ns;
+#endif
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const double s = ls_warp_sum(v[i]);
