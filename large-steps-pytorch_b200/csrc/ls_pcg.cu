@@ -152,11 +152,12 @@ size_t carve_handle(PcgHandle *h, char *base, int64_t V, int64_t nnz, int k_max,
     size_t o_col = c.take((size_t)(nnz + 8) * 4);
     size_t o_val = c.take((size_t)(nnz + 8) * 4);
     size_t o_dinv = c.take((size_t)Vp * 4);
-    size_t o_x = c.take((size_t)Vp * 4 * k_max);
+    const size_t k_rows = k_max < 4 ? 4 : k_max;   // x and the owner's p may be stored as rows of 4 floats (fused solver, RES = 1)
+    size_t o_x = c.take((size_t)Vp * 4 * k_rows);
     size_t o_r = c.take((size_t)Vp * 4 * k_max);
     size_t o_p = c.take((size_t)Vp * 4 * 4);            // p: rows of PW <= 4 floats
     size_t o_Ap = c.take((size_t)Vp * 4 * k_max);
-    size_t o_pown = c.take((size_t)Vp * 4 * k_max);
+    size_t o_pown = c.take((size_t)Vp * 4 * k_rows);
     size_t o_z2 = c.take((size_t)Vp * 4 * 4);
     size_t o_cy = c.take((size_t)Vp * 4 * k_max);
     size_t o_cd = c.take((size_t)Vp * 4 * k_max);
@@ -931,14 +932,14 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
     const int cheb = (K == 3 && h->cheb_m > 1) ? 1 : 0;
     const int pat = (K == 3 && h->pat_on) ? 1 : 0;
     const int W = lsp::PWARPS;
-    auto cap_slices = [&](int res, int dp) {   // slices per CTA that fit in shared memory at this residency level
+    auto cap_slices = [&](int res, int dp, int sync) {   // slices per CTA that fit in shared memory at this residency level
         if (res == 0) return 1 << 30;
         int n = 0;
-        while (lsf::fused_smem_bytes(K, res, n + 1, dp, cheb) <= (size_t)di.max_smem_optin) ++n;
+        while (lsf::fused_smem_bytes(K, res, n + 1, dp, cheb, sync) <= (size_t)di.max_smem_optin) ++n;
         return n;
     };
-    const int cap3 = cap_slices(3, pat), cap2 = cap_slices(2, 0), cap1 = cap_slices(1, 0);
-    const int cap4 = cheb ? 0 : (cap_slices(4, 0) < 63 ? cap_slices(4, 0) : 63);   // (63: the owner of a row is found by a 16-bit multiply)
+    const int cap3 = cap_slices(3, pat, 1), cap2c = cap_slices(2, 0, 1), cap2 = cap_slices(2, 0, 0), cap1 = cap_slices(1, 0, 0);
+    const int cap4 = cheb ? 0 : (cap_slices(4, 0, 1) < 63 ? cap_slices(4, 0, 1) : 63);   // (63: the owner of a row is found by a 16-bit multiply)
     const int want_cluster = env_int("LS_PCG_CLUSTER", -1);   // -1 auto, 0 never, N force cluster size N
     const int force_res = env_int("LS_PCG_RES", -1);
     // ---- one CTA (everything, including the gathered vector, in shared memory) or, on request, one cluster
@@ -951,7 +952,7 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
         if (h->nslices <= env_int("LS_PCG_ONECTA", W)) cs = 1;
         else if (!cheb && clres_regime(h->nslices)) cs = CLRES_CS;
         if (want_cluster > 0) cs = want_cluster;
-        if (cs > 0 && (h->nslices + cs - 1) / cs > cap2) cs = 0;
+        if (cs > 0 && (h->nslices + cs - 1) / cs > cap2c) cs = 0;
     }
     if (cs > 0) {
         const int nsl_max = (h->nslices + cs - 1) / cs;
@@ -962,9 +963,9 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
             if (K == 3 && nsl_max <= lsp::PT_SMALL / 32 && !(getenv("LS_PCG_SMALLCTA") && getenv("LS_PCG_SMALLCTA")[0] == '0')) nwc = lsp::PT_SMALL / 32;
         }
         if (res == 4 && !fused_fn(K, res, nwc, pat, 1, 0, cheb)) { res = 2; nwc = W; }
-        const int dp = (pat && nsl_max <= cap_slices(res, 1)) ? 1 : 0;
+        const int dp = (pat && nsl_max <= cap_slices(res, 1, 1)) ? 1 : 0;
         const void *fn = fused_fn(K, res, nwc, pat, 1, 0, cheb);
-        const size_t smem = lsf::fused_smem_bytes(K, res, nsl_max, dp, cheb);
+        const size_t smem = lsf::fused_smem_bytes(K, res, nsl_max, dp, cheb, 1);
         bool ok = fn != nullptr;
         if (ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin) != cudaSuccess) ok = false;
         if (ok && cs > 8 && cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = false;
@@ -1012,8 +1013,23 @@ int configure_fused(PcgHandle *h, const LsDevInfo &di, int K, PcgHandle::FusedCf
     if (K == 3 && res == 2 && nsl_max <= 16 && !(et && et[0] == '0')) nw = lsp::PT_SMALL / 32;
     const void *fn = fused_fn(K, res, nw, pat, 0, 0, cheb);
     if (!fn) return LS_OK;
-    const int dp = (pat && res >= 1 && nsl_max <= cap_slices(res, 1)) ? 1 : 0;
-    const size_t smem = lsf::fused_smem_bytes(K, res, nsl_max, dp, cheb);
+    int dp = (pat && res >= 1 && nsl_max <= cap_slices(res, 1, 0)) ? 1 : 0;
+    if (dp && res == 1) {
+        // L1 is what the shared-memory carve-out leaves of 256 KB, and the gathers re-use the published rows from it: if the kernel
+        // fits a smaller carve-out without the pattern diagonal in shared memory, leave the diagonal in global memory
+        // (V = 1e6: 196 instead of 228 KB, i.e. 60 instead of 28 KB of L1: 1.761 vs 1.775 ms, profiles/r02_l1_carveout_ab.jsonl)
+        auto carve_kb = [](size_t bytes) {
+            static const int steps[] = {8, 16, 32, 64, 100, 132, 164, 196, 228};
+            for (int st : steps)
+                if (bytes + 1024 <= (size_t)st * 1024) return st;
+            return 228;
+        };
+        if (carve_kb(lsf::fused_smem_bytes(K, res, nsl_max, 0, cheb, 0)) < carve_kb(lsf::fused_smem_bytes(K, res, nsl_max, 1, cheb, 0))) dp = 0;
+    }
+    const int dp_env = env_int("LS_PCG_DP", -1);   // A/B: 0 the diagonal stays in global memory, 1 in shared memory whenever it fits
+    if (dp_env == 0) dp = 0;
+    if (dp_env == 1) dp = (pat && res >= 1 && nsl_max <= cap_slices(res, 1, 0)) ? 1 : 0;
+    const size_t smem = lsf::fused_smem_bytes(K, res, nsl_max, dp, cheb, 0);
     // the attribute is per function and device, shared by every handle: always the device maximum, never a per-handle size
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, di.max_smem_optin) != cudaSuccess) {
         cudaGetLastError();
@@ -1370,7 +1386,7 @@ extern "C" int ls_pcg_create(void **handle_out, int64_t V, int64_t nnz, const in
         // cooperative grid at residency level 2 (measured: 4K..250K vertices 13-26 % faster, V = 1e6 13 % slower, one CTA slower)
         const int g = di.sm_count < h->nslices ? di.sm_count : h->nslices;
         const int nsl_max = (h->nslices + g - 1) / g;
-        const bool fits = lsf::fused_smem_bytes(3, 2, nsl_max, 1, 1) <= (size_t)di.max_smem_optin;
+        const bool fits = lsf::fused_smem_bytes(3, 2, nsl_max, 1, 1, 0) <= (size_t)di.max_smem_optin;
         precond = (h->nslices > env_int("LS_PCG_ONECTA", lsp::PWARPS) && fits) ? 2 : 1;
         // ... and not where one cluster holds everything in shared memory: a synchronisation costs a tenth there, plain CG's
         // fewer SpMVs win

@@ -37,6 +37,21 @@
 #ifndef LS_RING_SOA
 #define LS_RING_SOA 0     // A/B (build_variant.sh ringsoa -DLS_RING_SOA=1)
 #endif
+// Phase A "instruction diet" A/Bs (profiles/r02_phaseA_diet_ab.jsonl): both cut instructions (230 -> 188 per slice) and both made
+// the V = 1e6 solve SLOWER (1.782 -> 1.818 / 1.887 ms), neutral elsewhere: the phase is not issue-bound, and 16-byte x / p rows
+// cost what their 8 extra bytes per vector stream through the ~30 KB of L1 that is left next to 217 KB of shared memory.
+#ifndef LS_XP4
+#define LS_XP4 0          // RES = 1: x and the owner's p as rows of 4 floats (one 16-byte access each) instead of planes
+#endif
+#ifndef LS_FHADD
+#define LS_FHADD 0        // bf16 rows accumulated with mixed-precision adds (SASS FHADD.BF16) instead of unpack + FADD
+#endif
+#ifndef LS_Z_EL
+#define LS_Z_EL 0         // A/B: gathers of the published bf16 rows with L1::evict_last -- no effect (same file)
+#endif
+#ifndef LS_XP_STREAM
+#define LS_XP_STREAM 0    // x / p planes read and written with L1::no_allocate (so that they do not evict the published rows the gathers
+#endif                    // re-use from L1): 1.826 vs 1.774 ms at V = 1e6, general copy 2.21 vs 2.05 (profiles/r02_l1_hints_ab.jsonl) -- off
 #ifndef LS_POLL_FENCE
 #define LS_POLL_FENCE 0   // A/B (build_variant.sh pollfence -DLS_POLL_FENCE=1)
 #endif
@@ -318,9 +333,29 @@ __device__ __forceinline__ uint2 pack_bf16_row(float a, float b, float c) {
 __device__ __forceinline__ float4 unpack_bf16_row(const uint2 w) {
     return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16), 0.f);
 }
+// sum += the three bf16 components of a gathered row, in fp32: mixed-precision add (PTX add.rn.f32.bf16, SASS FHADD.BF16 with a
+// half selector) -- one instruction per component instead of unpack (shift / mask) + FADD
+__device__ __forceinline__ void acc_bf16_row(float &s0, float &s1, float &s2, const uint2 w) {
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %3;\n\tadd.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t"
+        "mov.b32 {lo, hi}, %4;\n\tadd.rn.f32.bf16 %2, lo, %2;\n\t}"
+        : "+f"(s0), "+f"(s1), "+f"(s2)
+        : "r"(w.x), "r"(w.y));
+}
+__device__ __forceinline__ float ld_stream_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_stream_f32(float *p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 __device__ __forceinline__ uint2 ld_coherent_u2(const uint2 *p) {
     uint2 v;
+#if LS_Z_EL
+    asm volatile("ld.global.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+#else
     asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+#endif
     return v;
 }
 
@@ -332,8 +367,11 @@ __host__ __device__ inline size_t fused_off_bytes(int nsl_max) { return ((size_t
 __host__ __device__ inline int fused_row_floats(int K, int res, int dp, int cheb = 0) {
     return (res == 0 ? 0 : (res == 1 ? 2 * K + 1 : (res == 2 ? 4 * K + 1 : 4 * K + 5))) + (dp ? 1 : 0) + ((cheb && res == 2) ? 2 * K : 0);
 }
-inline size_t fused_smem_bytes(int K, int res, int nsl_max, int dp = 0, int cheb = 0) {
-    return FUSED_SMEM_HDR + 2 * NVMAX * 16 * 8 + fused_off_bytes(nsl_max) + (size_t)nsl_max * 32u * 4u * fused_row_floats(K, res, dp, cheb);
+// the cluster exchange area exists only in the cluster instantiations: on the grid its 4 KB decide whether the V = 1e6 kernel fits
+// the 196 KB shared-memory carve-out (and leaves 60 KB of L1) or needs the 228 KB one (28 KB of L1)
+__host__ __device__ inline size_t fused_cl_bytes(int sync) { return sync == 1 ? (size_t)(2 * NVMAX * 16 * 8) : 0; }
+inline size_t fused_smem_bytes(int K, int res, int nsl_max, int dp, int cheb, int sync) {
+    return FUSED_SMEM_HDR + fused_cl_bytes(sync) + fused_off_bytes(nsl_max) + (size_t)nsl_max * 32u * 4u * fused_row_floats(K, res, dp, cheb);
 }
 
 template <int K, int RES, int NW, bool PAT, int SYNC, bool PROF, bool CHEB = false, bool ZH = false>
@@ -346,7 +384,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
     double *red = reinterpret_cast<double *>(smem_raw);                       // NV*32 + NV doubles, NV <= 16  (<= 4224 B)
     Scal *S = reinterpret_cast<Scal *>(smem_raw + 4352);
     double *cl = reinterpret_cast<double *>(smem_raw + FUSED_SMEM_HDR);       // [2][NVMAX][16]
-    int *off_s = reinterpret_cast<int *>(smem_raw + FUSED_SMEM_HDR + 2 * NVMAX * 16 * 8);   // [nsl_max + 1] general, then [nsl_max + 1] pattern
+    int *off_s = reinterpret_cast<int *>(smem_raw + FUSED_SMEM_HDR + fused_cl_bytes(SYNC));   // [nsl_max + 1] general, then [nsl_max + 1] pattern
     const int nsl_max = a.nsl_max;
     int *poff_s = off_s + (nsl_max + 1);
     float *fs = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(off_s) + fused_off_bytes(nsl_max));
@@ -390,8 +428,15 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
 
     auto R = [&](int li, int k, int row) -> float & { return RES ? r_s[((size_t)li * K + k) * 32 + lane] : a.r[(size_t)k * Vp + row]; };
     auto Sv = [&](int li, int k, int row) -> float & { return RES ? s_s[((size_t)li * K + k) * 32 + lane] : a.s[(size_t)k * Vp + row]; };
-    auto X = [&](int li, int k, int row) -> float & { return RES >= 2 ? x_s[((size_t)li * K + k) * 32 + lane] : a.x[(size_t)k * Vp + row]; };
-    auto P = [&](int li, int k, int row) -> float & { return RES >= 2 ? p_s[((size_t)li * K + k) * 32 + lane] : a.pv[(size_t)k * Vp + row]; };
+    // RES = 1 (x and the owner's p are the only vectors in global memory): rows of 4 floats, so that phase A moves each with one
+    // 16-byte access and one address computation -- the phase is bound by instruction issue and latency, not by bytes
+    constexpr bool XP4 = (RES == 1) && (LS_XP4 != 0);
+    auto X = [&](int li, int k, int row) -> float & {
+        return RES >= 2 ? x_s[((size_t)li * K + k) * 32 + lane] : (XP4 ? a.x[(size_t)row * 4 + k] : a.x[(size_t)k * Vp + row]);
+    };
+    auto P = [&](int li, int k, int row) -> float & {
+        return RES >= 2 ? p_s[((size_t)li * K + k) * 32 + lane] : (XP4 ? a.pv[(size_t)row * 4 + k] : a.pv[(size_t)k * Vp + row]);
+    };
     auto Dv = [&](int li, int row) -> float { return RES ? d_s[(size_t)li * 32 + lane] : a.dinv[row]; };
     // Chebyshev iterate (own rows) and direction: shared memory at RES = 2, else the direction lives in global planes and the
     // own row of the iterate is read back from its published copy
@@ -449,6 +494,29 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
             zh[row_] = w;
         } else {
             Zst(row_, make_float4(zz[0], zz[1], zz[2], zz[3]));
+        }
+    };
+
+    // one gathered row as loaded (bf16 rows stay packed until they are accumulated) and sum += row_a + row_b
+    constexpr bool RAW = ZH && (LS_FHADD != 0);
+    using GRow = typename std::conditional<RAW, uint2, float4>::type;
+    auto Zg = [&](int col) -> GRow {
+        if constexpr (RAW) {
+            if constexpr (RES == 4) {
+                uint2 w;
+                asm volatile("ld.shared::cluster.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(dsm_addr(col, 8u)) : "memory");
+                return w;
+            } else return ld_coherent_u2(zh + col);
+        } else return ZldP(col);
+    };
+    auto acc_pair = [&](float (&sum)[K], const GRow &ga, const GRow &gb) {
+        if constexpr (RAW) {
+            acc_bf16_row(sum[0], sum[1], sum[2], ga);
+            acc_bf16_row(sum[0], sum[1], sum[2], gb);
+        } else {
+            const float xk[4] = {ga.x + gb.x, ga.y + gb.y, ga.z + gb.z, ga.w + gb.w};
+#pragma unroll
+            for (int k = 0; k < K; ++k) sum[k] += xk[k];
         }
     };
 
@@ -528,11 +596,11 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 float dp;
                 auto body = [&](auto ub_tag) {
                     constexpr int UB = decltype(ub_tag)::value;
-                    float4 xa[UB], xb[UB];
+                    GRow xa[UB], xb[UB];
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
-                        xa[u] = ZldP(cv[u].x);
-                        xb[u] = ZldP(cv[u].y);
+                        xa[u] = Zg(cv[u].x);
+                        xb[u] = Zg(cv[u].y);
                     }
                     zo = own(li, row);
                     dp = dp_smem ? dp_s[(size_t)li * 32 + lane] : a.diagp[row];
@@ -545,11 +613,7 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                             nv[u] = (u < wn) ? ld_ent<KEEP>(en + u * 32) : make_int2(sn * 32 + lane, sn * 32 + lane);
                     }
 #pragma unroll
-                    for (int u = 0; u < UB; ++u) {
-                        const float xk[4] = {xa[u].x + xb[u].x, xa[u].y + xb[u].y, xa[u].z + xb[u].z, xa[u].w + xb[u].w};
-#pragma unroll
-                        for (int k = 0; k < K; ++k) sum[k] += xk[k];
-                    }
+                    for (int u = 0; u < UB; ++u) acc_pair(sum, xa[u], xb[u]);
                     const int extra = 2 * (UB - min(w2, UB));
                     dp = fmaf(-a.offc, (float)extra, dp);
                 };
@@ -558,18 +622,14 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 for (int j = U; j < w2; j += U) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) cv[u] = (j + u < w2) ? ld_ent<KEEP>(e + (j + u) * 32) : make_int2(row, row);
-                    float4 xa[U], xb[U];
+                    GRow xa[U], xb[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        xa[u] = ZldP(cv[u].x);
-                        xb[u] = ZldP(cv[u].y);
+                        xa[u] = Zg(cv[u].x);
+                        xb[u] = Zg(cv[u].y);
                     }
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const float xk[4] = {xa[u].x + xb[u].x, xa[u].y + xb[u].y, xa[u].z + xb[u].z, xa[u].w + xb[u].w};
-#pragma unroll
-                        for (int k = 0; k < K; ++k) sum[k] += xk[k];
-                    }
+                    for (int u = 0; u < U; ++u) acc_pair(sum, xa[u], xb[u]);
                     const int extra = 2 * max(0, j + U - w2);
                     dp = fmaf(-a.offc, (float)extra, dp);
                 }
@@ -936,24 +996,58 @@ __global__ void __launch_bounds__(NW * 32, 1) pcg_fused_kernel(const FusedArgs a
                 float po[K], xo[K];
                 spmv_pass(
                     [&](int li, int row) {
+                        if constexpr (XP4) {
+                            const float4 p4 = *reinterpret_cast<const float4 *>(a.pv + 4 * (size_t)row);
+                            const float4 x4 = *reinterpret_cast<const float4 *>(a.x + 4 * (size_t)row);
+                            const float pk[4] = {p4.x, p4.y, p4.z, p4.w}, xk[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            po[k] = P(li, k, row);
-                            xo[k] = X(li, k, row);
+                            for (int k = 0; k < K; ++k) {
+                                po[k] = pk[k];
+                                xo[k] = xk[k];
+                            }
+                        } else if constexpr (RES < 2 && LS_XP_STREAM != 0) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                po[k] = ld_stream_f32(&P(li, k, row));
+                                xo[k] = ld_stream_f32(&X(li, k, row));
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                po[k] = P(li, k, row);
+                                xo[k] = X(li, k, row);
+                            }
                         }
                     },
                     own_z,
                     [&](int li, int row, const float (&w_)[K], const float4 &zo) {
                         const float zk[4] = {zo.x, zo.y, zo.z, zo.w};
+                        float xn[4] = {0.f, 0.f, 0.f, 0.f}, pn4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
                             const float al = S->alpha[k], be = S->beta[k];
-                            X(li, k, row) = fmaf(al, po[k], xo[k]);               // x += alpha_prev p   (the previous iteration's pair)
+                            xn[k] = fmaf(al, po[k], xo[k]);                         // x += alpha_prev p   (the previous iteration's pair)
                             const float pn = fmaf(be, po[k], zk[k]);                // p = z + beta p
                             const float sn_ = fmaf(be, Sv(li, k, row), w_[k]);      // s = A z + beta s  (= A p)
-                            P(li, k, row) = pn;
+                            pn4[k] = pn;
                             Sv(li, k, row) = sn_;
                             dacc_f[k] = fmaf(pn, sn_, dacc_f[k]);
+                        }
+                        if constexpr (XP4) {
+                            *reinterpret_cast<float4 *>(a.x + 4 * (size_t)row) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+                            *reinterpret_cast<float4 *>(a.pv + 4 * (size_t)row) = make_float4(pn4[0], pn4[1], pn4[2], pn4[3]);
+                        } else if constexpr (RES < 2 && LS_XP_STREAM != 0) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                st_stream_f32(&X(li, k, row), xn[k]);
+                                st_stream_f32(&P(li, k, row), pn4[k]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                X(li, k, row) = xn[k];
+                                P(li, k, row) = pn4[k];
+                            }
                         }
                     });
                 double dacc[K];
