@@ -118,6 +118,25 @@ def test_column_counts(k):
     assert rel_l2(x.cpu().numpy(), ds.solve(b)) < BAR
 
 
+@pytest.mark.parametrize("res", ["2", "1", "0"])
+def test_two_and_four_columns_on_the_cooperative_grid(res, monkeypatch):
+    """k = 4 runs the 4-column instantiations of the fused kernel, k = 2 the 3-column ones with a runtime column count; here on
+    the cooperative grid at every residency level (test_column_counts covers the one-CTA path)."""
+    monkeypatch.setenv("LS_PCG_RES", res)
+    v, f = workloads.plane(120, seed=3)
+    kw = dict(lambda_=1.0, alpha=0.9)
+    (r, c, val, V), ds = direct_for(v, f, kw)
+    M = compute_matrix(*to_dev(v, f), **kw)
+    s = PCGSolver(M)
+    d = s.describe()
+    assert d["algo"] == "fused" and d["cluster"] == 0 and d["residency"] == int(res)
+    for k in (4, 2):
+        b = np.random.default_rng(k).normal(size=(V, k)).astype(np.float32)
+        x = s.solve(t(b))
+        assert x.shape == (V, k) and s.status == 1
+        assert rel_l2(x.cpu().numpy(), ds.solve(b)) < BAR
+
+
 def test_columns_freeze_independently_and_zero_rhs():
     v, f = workloads.icosphere(3)
     (r, c, val, V), ds = direct_for(v, f, dict(lambda_=10.0))
